@@ -193,6 +193,20 @@ def compute_boundaries(program):
             inner_id += 1
 
 
+def group_reach(group):
+    """How far beyond its tile a fused group touches every field it reads or writes.
+
+    Same backward sweep as ``_extents``; returns ``field -> box`` for the group's inputs
+    (the haloed tile a kernel must stage) and for its stencils (equal to ``LOOPS``).
+    """
+    reach = {name: ZERO_BOX for name in group["OUTPUTS"]}
+    for stencil in reversed(group["STENCILS"]):
+        for field, box in stencil["OFFSETS"].items():
+            grown = box_add(box, reach[stencil["NAME"]])
+            reach[field] = box_widen(reach[field], grown) if field in reach else grown
+    return reach
+
+
 def ceil_div(a, b):
     return (a + b - 1) // b
 

@@ -1,0 +1,778 @@
+// absinthe_b200 launcher: the C ABI of include/absinthe_b200.h.
+//
+// One shared library, built once (see __graft_entry__.build), drives every generated variant.
+// A variant arrives as (descriptor text, sm_100a cubin): the descriptor lists the global fields,
+// the fused-group kernels with their launch shapes and parameter-block layout (TMA tensor maps
+// and field pointers), and the fields that need a periodic halo update after each group.  The
+// launcher loads the cubin through the driver API (entry points are resolved at run time with
+// cudaGetDriverEntryPoint, so the library has no link-time dependency on libcuda and can be
+// dlopen'ed on a machine without a GPU), encodes the tensor maps against the bound buffers and
+// replays the group sequence -- optionally as one CUDA graph -- on the caller's stream.
+//
+// Reference lines each piece replaces are cited in include/absinthe_b200.h.
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "../../include/absinthe_b200.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code ? code : -1;
+}
+
+#define RT(call)                                                                           \
+    do {                                                                                   \
+        cudaError_t e_ = (call);                                                           \
+        if (e_ != cudaSuccess)                                                             \
+            return fail((int)e_, "%s failed: %s", #call, cudaGetErrorString(e_));          \
+    } while (0)
+
+// ---- driver API, resolved lazily ---------------------------------------------------------
+struct Driver {
+    CUresult (*ModuleLoadData)(CUmodule*, const void*) = nullptr;
+    CUresult (*ModuleUnload)(CUmodule) = nullptr;
+    CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
+    CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
+    CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
+                             unsigned, CUstream, void**, void**) = nullptr;
+    CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                     const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                     const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
+    CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    bool ready = false;
+};
+Driver g_drv;
+
+template <typename F>
+int resolve(const char* name, F& slot) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult status;
+    cudaError_t e = cudaGetDriverEntryPoint(name, &fn, cudaEnableDefault, &status);
+    if (e != cudaSuccess || status != cudaDriverEntryPointSuccess || fn == nullptr)
+        return fail((int)e, "driver entry point %s unavailable (%s)", name, cudaGetErrorString(e));
+    slot = reinterpret_cast<F>(fn);
+    return 0;
+}
+
+int driver() {
+    if (g_drv.ready) return 0;
+    int rc = 0;
+    if ((rc = resolve("cuModuleLoadData", g_drv.ModuleLoadData))) return rc;
+    if ((rc = resolve("cuModuleUnload", g_drv.ModuleUnload))) return rc;
+    if ((rc = resolve("cuModuleGetFunction", g_drv.ModuleGetFunction))) return rc;
+    if ((rc = resolve("cuFuncSetAttribute", g_drv.FuncSetAttribute))) return rc;
+    if ((rc = resolve("cuOccupancyMaxActiveBlocksPerMultiprocessor",
+                      g_drv.OccupancyMaxActiveBlocksPerMultiprocessor))) return rc;
+    if ((rc = resolve("cuLaunchKernel", g_drv.LaunchKernel))) return rc;
+    if ((rc = resolve("cuTensorMapEncodeTiled", g_drv.TensorMapEncodeTiled))) return rc;
+    if ((rc = resolve("cuGetErrorString", g_drv.GetErrorString))) return rc;
+    g_drv.ready = true;
+    return 0;
+}
+
+const char* drv_error(CUresult r) {
+    const char* msg = nullptr;
+    if (g_drv.GetErrorString && g_drv.GetErrorString(r, &msg) == CUDA_SUCCESS && msg) return msg;
+    return "unknown driver error";
+}
+
+#define DRV(call)                                                                          \
+    do {                                                                                   \
+        CUresult r_ = (call);                                                              \
+        if (r_ != CUDA_SUCCESS) return fail((int)r_, "%s failed: %s", #call, drv_error(r_)); \
+    } while (0)
+
+// ---- generic device kernels ----------------------------------------------------------------
+
+struct Geometry {
+    int X, Y, Z, HX, HY, HZ;
+    __host__ __device__ long row() const { return X + 2L * HX; }
+    __host__ __device__ long rows() const { return Y + 2L * HY; }
+    __host__ __device__ long planes() const { return Z + 2L * HZ; }
+    __host__ __device__ long plane() const { return row() * rows(); }
+    __host__ __device__ long cells() const { return plane() * planes(); }
+};
+
+constexpr int kMaxHaloFields = 16;
+struct FieldList {
+    double* ptr[kMaxHaloFields];
+    int count;
+};
+
+__device__ __forceinline__ int wrap(int p, int h, int s) {
+    // padded index -> the interior padded index it mirrors (needs s >= h)
+    return p < h ? p + s : (p >= h + s ? p - s : p);
+}
+
+// Closed form of make_periodic (ref template_tiling.cpp:136-159): after the i, j, k passes every
+// halo cell holds the interior value at the wrapped coordinates.  One launch updates all outputs
+// of a group.  mask: bit0 = i faces, bit1 = j faces, bit2 = k faces.  Valid when each extent is at
+// least as large as its halo.
+__global__ void periodic_kernel(FieldList fields, Geometry g, int mask) {
+    const long row = g.row(), rows = g.rows(), plane = g.plane();
+    // three slabs of halo cells, enumerated i-fastest
+    const long nk = (mask & 4) ? 2L * g.HZ * plane : 0;                    // k faces: full planes
+    const long nj = (mask & 2) ? (long)g.Z * 2 * g.HY * row : 0;          // j faces: interior k
+    const long ni = (mask & 1) ? (long)g.Z * g.Y * 2 * g.HX : 0;          // i faces: interior j,k
+    const long total = nk + nj + ni;
+    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < total;
+         n += (long)gridDim.x * blockDim.x) {
+        int i, j, k;
+        if (n < nk) {
+            long kk = n / plane, r = n % plane;
+            k = kk < g.HZ ? (int)kk : (int)(kk + g.Z);
+            j = (int)(r / row);
+            i = (int)(r % row);
+        } else if (n < nk + nj) {
+            long m = n - nk;
+            long per_k = 2L * g.HY * row;
+            k = g.HZ + (int)(m / per_k);
+            long r = m % per_k;
+            long jj = r / row;
+            j = jj < g.HY ? (int)jj : (int)(jj + g.Y);
+            i = (int)(r % row);
+        } else {
+            long m = n - nk - nj;
+            long per_k = (long)g.Y * 2 * g.HX;
+            k = g.HZ + (int)(m / per_k);
+            long r = m % per_k;
+            j = g.HY + (int)(r / (2 * g.HX));
+            long ii = r % (2 * g.HX);
+            i = ii < g.HX ? (int)ii : (int)(ii + g.X);
+        }
+        int si = (mask & 1) ? wrap(i, g.HX, g.X) : i;
+        int sj = (mask & 2) ? wrap(j, g.HY, g.Y) : j;
+        int sk = (mask & 4) ? wrap(k, g.HZ, g.Z) : k;
+        const long dst = i + j * row + k * plane;
+        const long src = si + sj * row + sk * plane;
+        for (int f = 0; f < fields.count; ++f) fields.ptr[f][dst] = fields.ptr[f][src];
+    }
+}
+
+// Literal three-pass version for degenerate domains (an extent smaller than its halo), where the
+// sequential copies of the reference read cells written earlier in the same pass.
+__global__ void periodic_pass_kernel(double* data, Geometry g, int pass) {
+    const long row = g.row(), rows = g.rows(), planes = g.planes(), plane = g.plane();
+    const long lines = pass == 0 ? rows * planes : (pass == 1 ? row * planes : row * rows);
+    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < lines;
+         n += (long)gridDim.x * blockDim.x) {
+        if (pass == 0) {
+            double* p = data + n * row;
+            for (int i = 0; i < g.HX; ++i) { p[i] = p[i + g.X]; p[i + g.X + g.HX] = p[i + g.HX]; }
+        } else if (pass == 1) {
+            double* p = data + (n / row) * plane + (n % row);
+            for (int j = 0; j < g.HY; ++j) {
+                p[j * row] = p[(j + g.Y) * row];
+                p[(j + g.Y + g.HY) * row] = p[(j + g.HY) * row];
+            }
+        } else {
+            double* p = data + n;
+            for (int k = 0; k < g.HZ; ++k) {
+                p[k * plane] = p[(k + g.Z) * plane];
+                p[(k + g.Z + g.HZ) * plane] = p[(k + g.HZ) * plane];
+            }
+        }
+    }
+}
+
+__global__ void flush_kernel(double* buf, long n, double v) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        buf[i] = v;
+}
+
+// rows [j0, j0+width) of every plane <-> dense [planes][width][row]
+__global__ void pack_kernel(const double* __restrict__ field, double* __restrict__ buffer, Geometry g,
+                            int j0, int width, int unpack) {
+    const long row = g.row(), plane = g.plane();
+    const long total = g.planes() * width * row;
+    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < total;
+         n += (long)gridDim.x * blockDim.x) {
+        long k = n / (width * row), r = n % (width * row);
+        long at = k * plane + (j0 + r / row) * row + r % row;
+        if (unpack) const_cast<double*>(field)[at] = buffer[n];
+        else buffer[n] = field[at];
+    }
+}
+
+int launch_grid(long items, int threads) {
+    long blocks = (items + threads - 1) / threads;
+    return (int)std::max(1L, std::min(blocks, 148L * 16));
+}
+
+int periodic_update(const FieldList& fields, const Geometry& g, int mask, cudaStream_t stream) {
+    if (fields.count == 0) return 0;
+    const bool regular = g.X >= g.HX && g.Y >= g.HY && g.Z >= g.HZ;
+    if (regular) {
+        long total = 2L * g.HZ * g.plane() + (long)g.Z * 2 * g.HY * g.row() + (long)g.Z * g.Y * 2 * g.HX;
+        periodic_kernel<<<launch_grid(total, 256), 256, 0, stream>>>(fields, g, mask);
+    } else {
+        for (int f = 0; f < fields.count; ++f)
+            for (int pass = 0; pass < 3; ++pass) {
+                if (!(mask & (1 << pass))) continue;
+                long lines = pass == 0 ? g.rows() * g.planes()
+                                       : (pass == 1 ? g.row() * g.planes() : g.row() * g.rows());
+                periodic_pass_kernel<<<launch_grid(lines, 128), 128, 0, stream>>>(fields.ptr[f], g, pass);
+            }
+    }
+    RT(cudaGetLastError());
+    return 0;
+}
+
+// ---- variant -------------------------------------------------------------------------------
+
+enum FieldKind { kInput = 0, kOutput = 1, kTemp = 2 };
+
+struct Field {
+    std::string name;
+    FieldKind kind;
+    double* ptr = nullptr;
+    bool owned = false;
+};
+
+struct Arg {
+    enum Type { kMap, kPtr, kTileCtl, kScratch } type;
+    size_t offset;
+    int field = -1;
+    unsigned box[3] = {0, 0, 0};
+};
+
+struct Group {
+    int id = 0;
+    std::string symbol;
+    int threads = 0;
+    size_t smem = 0;
+    int tiles = 0;
+    size_t params_bytes = 0;
+    size_t scratch_bytes = 0;      // per resident CTA
+    int training_step = 20;
+    int fused_halo = 0;
+    std::vector<Arg> args;
+    std::vector<int> halo_fields;
+    CUfunction fn = nullptr;
+    int blocks_per_sm = 1;
+    std::vector<unsigned char> params;
+    double* scratch = nullptr;
+};
+
+}  // namespace
+
+struct absinthe_variant {
+    std::string name;
+    Geometry geo{};
+    int device = 0;
+    int sms = 148;
+    std::vector<Field> fields;
+    std::vector<int> inputs, outputs;
+    std::vector<Group> groups;
+    CUmodule module = nullptr;
+    bool bound = false;
+    cudaGraphExec_t graph = nullptr;
+    cudaStream_t graph_stream = nullptr;
+    std::vector<cudaEvent_t> events;
+};
+
+namespace {
+
+double* g_flush = nullptr;
+const long kFlushDoubles = 48L * 1024 * 1024;  // 384 MB > 2 x L2
+
+int find_field(const absinthe_variant* v, const std::string& name) {
+    for (size_t n = 0; n < v->fields.size(); ++n)
+        if (v->fields[n].name == name) return (int)n;
+    return -1;
+}
+
+int parse_descriptor(absinthe_variant* v, const char* text) {
+    std::istringstream in(text);
+    std::string line;
+    Group* group = nullptr;
+    bool header = false;
+    while (std::getline(in, line)) {
+        std::istringstream ls(line);
+        std::string key;
+        if (!(ls >> key) || key[0] == '#') continue;
+        if (key == "absinthe-variant") {
+            int version = 0;
+            ls >> version;
+            if (version != ABSINTHE_ABI_VERSION) return fail(-2, "descriptor version %d unsupported", version);
+            header = true;
+        } else if (key == "name") {
+            ls >> v->name;
+        } else if (key == "domain") {
+            ls >> v->geo.X >> v->geo.Y >> v->geo.Z >> v->geo.HX >> v->geo.HY >> v->geo.HZ;
+        } else if (key == "field") {
+            Field f;
+            std::string kind;
+            ls >> f.name >> kind;
+            f.kind = kind == "in" ? kInput : (kind == "out" ? kOutput : kTemp);
+            if (f.kind == kInput) v->inputs.push_back((int)v->fields.size());
+            if (f.kind == kOutput) v->outputs.push_back((int)v->fields.size());
+            v->fields.push_back(f);
+        } else if (key == "group") {
+            v->groups.emplace_back();
+            group = &v->groups.back();
+            std::string tok;
+            ls >> group->id;
+            while (ls >> tok) {
+                if (tok == "kernel") ls >> group->symbol;
+                else if (tok == "threads") ls >> group->threads;
+                else if (tok == "smem") ls >> group->smem;
+                else if (tok == "tiles") ls >> group->tiles;
+                else if (tok == "params") ls >> group->params_bytes;
+                else if (tok == "scratch") ls >> group->scratch_bytes;
+                else if (tok == "training_step") ls >> group->training_step;
+                else if (tok == "fused_halo") ls >> group->fused_halo;
+                else return fail(-2, "descriptor: unknown group attribute '%s'", tok.c_str());
+            }
+        } else if (key == "arg") {
+            if (!group) return fail(-2, "descriptor: arg outside group");
+            Arg a{};
+            std::string type, name;
+            ls >> type >> a.offset;
+            if (type == "tmap") {
+                a.type = Arg::kMap;
+                ls >> name >> a.box[0] >> a.box[1] >> a.box[2];
+            } else if (type == "ptr") {
+                a.type = Arg::kPtr;
+                ls >> name;
+            } else if (type == "tilectl") {
+                a.type = Arg::kTileCtl;
+            } else if (type == "scratch") {
+                a.type = Arg::kScratch;
+            } else {
+                return fail(-2, "descriptor: unknown arg type '%s'", type.c_str());
+            }
+            if (!name.empty()) {
+                a.field = find_field(v, name);
+                if (a.field < 0) return fail(-2, "descriptor: unknown field '%s'", name.c_str());
+            }
+            group->args.push_back(a);
+        } else if (key == "halo") {
+            if (!group) return fail(-2, "descriptor: halo outside group");
+            std::string name;
+            ls >> name;
+            int f = find_field(v, name);
+            if (f < 0) return fail(-2, "descriptor: unknown halo field '%s'", name.c_str());
+            group->halo_fields.push_back(f);
+        } else if (key == "endgroup") {
+            group = nullptr;
+        } else if (key == "end") {
+            break;
+        }
+    }
+    if (!header) return fail(-2, "descriptor: missing 'absinthe-variant' header");
+    if (v->geo.X <= 0 || v->geo.Y <= 0 || v->geo.Z <= 0) return fail(-2, "descriptor: bad domain");
+    for (auto& g : v->groups)
+        if ((int)g.halo_fields.size() > kMaxHaloFields)
+            return fail(-2, "group %d has more than %d halo fields", g.id, kMaxHaloFields);
+    return 0;
+}
+
+int encode_map(const absinthe_variant* v, const Arg& a, double* base, CUtensorMap* map) {
+    const Geometry& g = v->geo;
+    cuuint64_t dims[3] = {(cuuint64_t)g.row(), (cuuint64_t)g.rows(), (cuuint64_t)g.planes()};
+    cuuint64_t strides[2] = {(cuuint64_t)g.row() * 8, (cuuint64_t)g.plane() * 8};
+    cuuint32_t box[3] = {a.box[0], a.box[1], a.box[2]};
+    cuuint32_t elem[3] = {1, 1, 1};
+    DRV(g_drv.TensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box,
+                                   elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+    return 0;
+}
+
+int grid_for(const absinthe_variant* v, const Group& g, int tiles) {
+    int resident = std::max(1, g.blocks_per_sm) * v->sms;
+    return std::max(1, std::min(tiles, resident));
+}
+
+int build_params(absinthe_variant* v, Group& g) {
+    g.params.assign(g.params_bytes, 0);
+    for (const Arg& a : g.args) {
+        if (a.type == Arg::kMap) {
+            CUtensorMap map;
+            int rc = encode_map(v, a, v->fields[a.field].ptr, &map);
+            if (rc) return rc;
+            std::memcpy(g.params.data() + a.offset, &map, sizeof(map));
+        } else if (a.type == Arg::kPtr) {
+            double* p = v->fields[a.field].ptr;
+            std::memcpy(g.params.data() + a.offset, &p, sizeof(p));
+        } else if (a.type == Arg::kScratch) {
+            std::memcpy(g.params.data() + a.offset, &g.scratch, sizeof(g.scratch));
+        }
+    }
+    return 0;
+}
+
+void set_tilectl(Group& g, int step, int count) {
+    for (const Arg& a : g.args)
+        if (a.type == Arg::kTileCtl) {
+            int ctl[2] = {step, count};
+            std::memcpy(g.params.data() + a.offset, ctl, sizeof(ctl));
+        }
+}
+
+int launch_group(absinthe_variant* v, Group& g, bool training, cudaStream_t stream) {
+    int step = training ? g.training_step : 1;
+    int count = (g.tiles + step - 1) / step;
+    set_tilectl(g, step, count);
+    void* params[1] = {g.params.data()};
+    int grid = grid_for(v, g, count);
+    DRV(g_drv.LaunchKernel(g.fn, grid, 1, 1, g.threads, 1, 1, (unsigned)g.smem, (CUstream)stream,
+                           params, nullptr));
+    return 0;
+}
+
+int halo_group(absinthe_variant* v, Group& g, cudaStream_t stream) {
+    if (g.fused_halo || g.halo_fields.empty()) return 0;
+    FieldList list{};
+    list.count = (int)g.halo_fields.size();
+    for (int n = 0; n < list.count; ++n) list.ptr[n] = v->fields[g.halo_fields[n]].ptr;
+    return periodic_update(list, v->geo, 7, stream);
+}
+
+int require_bound(const absinthe_variant* v) {
+    if (!v) return fail(-3, "null variant");
+    if (!v->bound) return fail(-3, "variant '%s' has no buffers bound", v->name.c_str());
+    return 0;
+}
+
+}  // namespace
+
+// ---- C ABI ---------------------------------------------------------------------------------
+
+extern "C" {
+
+int absinthe_abi_version(void) { return ABSINTHE_ABI_VERSION; }
+
+const char* absinthe_last_error(void) { return g_error.c_str(); }
+
+int absinthe_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        fail((int)e, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+        return -(int)e;
+    }
+    return n;
+}
+
+int absinthe_variant_load(const char* descriptor, const void* cubin, size_t cubin_bytes, int device,
+                          absinthe_variant** out) {
+    if (!descriptor || !cubin || !cubin_bytes || !out) return fail(-1, "absinthe_variant_load: null argument");
+    *out = nullptr;
+    RT(cudaSetDevice(device));
+    RT(cudaFree(nullptr));
+    int rc = driver();
+    if (rc) return rc;
+    absinthe_variant* v = new absinthe_variant();
+    v->device = device;
+    rc = parse_descriptor(v, descriptor);
+    if (rc) { delete v; return rc; }
+    cudaDeviceProp prop;
+    cudaError_t e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { delete v; return fail((int)e, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
+    v->sms = prop.multiProcessorCount;
+    CUresult r = g_drv.ModuleLoadData(&v->module, cubin);
+    if (r != CUDA_SUCCESS) { delete v; return fail((int)r, "cuModuleLoadData failed: %s (is the cubin built for sm_%d%d?)", drv_error(r), prop.major, prop.minor); }
+    for (Group& g : v->groups) {
+        r = g_drv.ModuleGetFunction(&g.fn, v->module, g.symbol.c_str());
+        if (r != CUDA_SUCCESS) { absinthe_variant_free(v); return fail((int)r, "kernel %s not found: %s", g.symbol.c_str(), drv_error(r)); }
+        if (g.smem > 48 * 1024) {
+            r = g_drv.FuncSetAttribute(g.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)g.smem);
+            if (r != CUDA_SUCCESS) { absinthe_variant_free(v); return fail((int)r, "kernel %s: %zu bytes of shared memory refused: %s", g.symbol.c_str(), g.smem, drv_error(r)); }
+        }
+        int blocks = 0;
+        r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&blocks, g.fn, g.threads, g.smem);
+        if (r != CUDA_SUCCESS || blocks < 1) { absinthe_variant_free(v); return fail((int)r, "kernel %s cannot be resident (threads %d, smem %zu)", g.symbol.c_str(), g.threads, g.smem); }
+        g.blocks_per_sm = blocks;
+        if (g.scratch_bytes) {
+            size_t total = g.scratch_bytes * (size_t)grid_for(v, g, g.tiles);
+            e = cudaMalloc(&g.scratch, total);
+            if (e != cudaSuccess) { absinthe_variant_free(v); return fail((int)e, "scratch allocation of %zu bytes failed", total); }
+        }
+    }
+    // inter-group temporaries are owned by the library (zero-initialised like sarray_3d(0.0))
+    for (Field& f : v->fields)
+        if (f.kind == kTemp) {
+            size_t bytes = (size_t)v->geo.cells() * 8;
+            e = cudaMalloc(&f.ptr, bytes);
+            if (e != cudaSuccess) { absinthe_variant_free(v); return fail((int)e, "temporary '%s': %zu bytes refused", f.name.c_str(), bytes); }
+            cudaMemset(f.ptr, 0, bytes);
+            f.owned = true;
+        }
+    *out = v;
+    return 0;
+}
+
+void absinthe_variant_free(absinthe_variant* v) {
+    if (!v) return;
+    cudaSetDevice(v->device);
+    if (v->graph) cudaGraphExecDestroy(v->graph);
+    for (cudaEvent_t e : v->events) cudaEventDestroy(e);
+    for (Field& f : v->fields)
+        if (f.owned && f.ptr) cudaFree(f.ptr);
+    for (Group& g : v->groups)
+        if (g.scratch) cudaFree(g.scratch);
+    if (v->module && g_drv.ModuleUnload) g_drv.ModuleUnload(v->module);
+    delete v;
+}
+
+int absinthe_variant_info(const absinthe_variant* v, int dims[6], int* n_inputs, int* n_outputs,
+                          int* n_groups) {
+    if (!v) return fail(-3, "null variant");
+    if (dims) {
+        dims[0] = v->geo.X; dims[1] = v->geo.Y; dims[2] = v->geo.Z;
+        dims[3] = v->geo.HX; dims[4] = v->geo.HY; dims[5] = v->geo.HZ;
+    }
+    if (n_inputs) *n_inputs = (int)v->inputs.size();
+    if (n_outputs) *n_outputs = (int)v->outputs.size();
+    if (n_groups) *n_groups = (int)v->groups.size();
+    return 0;
+}
+
+const char* absinthe_variant_field(const absinthe_variant* v, int is_output, int idx) {
+    if (!v) return nullptr;
+    const std::vector<int>& list = is_output ? v->outputs : v->inputs;
+    if (idx < 0 || idx >= (int)list.size()) return nullptr;
+    return v->fields[list[idx]].name.c_str();
+}
+
+size_t absinthe_variant_field_bytes(const absinthe_variant* v) {
+    return v ? (size_t)v->geo.cells() * 8 : 0;
+}
+
+int absinthe_variant_launches(const absinthe_variant* v) {
+    if (!v) return 0;
+    int n = 0;
+    for (const Group& g : v->groups) {
+        n += 1;
+        if (!g.fused_halo && !g.halo_fields.empty()) {
+            const Geometry& q = v->geo;
+            bool regular = q.X >= q.HX && q.Y >= q.HY && q.Z >= q.HZ;
+            n += regular ? 1 : 3 * (int)g.halo_fields.size();
+        }
+    }
+    return n;
+}
+
+int absinthe_variant_fused_halo(const absinthe_variant* v) {
+    if (!v) return 0;
+    for (const Group& g : v->groups)
+        if (!g.fused_halo && !g.halo_fields.empty()) return 0;
+    return 1;
+}
+
+int absinthe_variant_bind(absinthe_variant* v, const double* const* d_inputs, double* const* d_outputs) {
+    if (!v) return fail(-3, "null variant");
+    RT(cudaSetDevice(v->device));
+    for (size_t n = 0; n < v->inputs.size(); ++n) {
+        if (!d_inputs || !d_inputs[n]) return fail(-3, "input %zu is null", n);
+        v->fields[v->inputs[n]].ptr = const_cast<double*>(d_inputs[n]);
+    }
+    for (size_t n = 0; n < v->outputs.size(); ++n) {
+        if (!d_outputs || !d_outputs[n]) return fail(-3, "output %zu is null", n);
+        v->fields[v->outputs[n]].ptr = d_outputs[n];
+    }
+    for (Group& g : v->groups) {
+        int rc = build_params(v, g);
+        if (rc) return rc;
+    }
+    if (v->graph) { cudaGraphExecDestroy(v->graph); v->graph = nullptr; }
+    v->bound = true;
+    return 0;
+}
+
+int absinthe_variant_apply(absinthe_variant* v, void* stream) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    for (Group& g : v->groups) {
+        if ((rc = launch_group(v, g, false, s))) return rc;
+        if ((rc = halo_group(v, g, s))) return rc;
+    }
+    return 0;
+}
+
+int absinthe_variant_apply_graph(absinthe_variant* v, void* stream) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!v->graph || v->graph_stream != s) {
+        if (v->graph) { cudaGraphExecDestroy(v->graph); v->graph = nullptr; }
+        cudaGraph_t graph = nullptr;
+        RT(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        rc = absinthe_variant_apply(v, s);
+        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail((int)e, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&v->graph, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return fail((int)e, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+        v->graph_stream = s;
+    }
+    RT(cudaGraphLaunch(v->graph, s));
+    return 0;
+}
+
+int absinthe_variant_apply_group(absinthe_variant* v, int group, int with_halo, void* stream) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    for (Group& g : v->groups)
+        if (g.id == group) {
+            if ((rc = launch_group(v, g, false, (cudaStream_t)stream))) return rc;
+            return with_halo ? halo_group(v, g, (cudaStream_t)stream) : 0;
+        }
+    return fail(-3, "variant '%s' has no group %d", v->name.c_str(), group);
+}
+
+int absinthe_variant_group_outputs(const absinthe_variant* v, int group) {
+    if (!v) return 0;
+    for (const Group& g : v->groups)
+        if (g.id == group) return (int)g.halo_fields.size();
+    return 0;
+}
+
+const char* absinthe_variant_group_output(const absinthe_variant* v, int group, int idx) {
+    if (!v) return nullptr;
+    for (const Group& g : v->groups)
+        if (g.id == group && idx >= 0 && idx < (int)g.halo_fields.size())
+            return v->fields[g.halo_fields[idx]].name.c_str();
+    return nullptr;
+}
+
+double* absinthe_variant_field_ptr(const absinthe_variant* v, const char* name) {
+    if (!v || !name) return nullptr;
+    int f = find_field(v, name);
+    return f < 0 ? nullptr : v->fields[f].ptr;
+}
+
+int absinthe_flush_l2(void* stream) {
+    if (!g_flush) RT(cudaMalloc(&g_flush, kFlushDoubles * 8));
+    flush_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(g_flush, kFlushDoubles, 0.0);
+    RT(cudaGetLastError());
+    return 0;
+}
+
+int absinthe_variant_run(absinthe_variant* v, void* stream, int runs, int flush, int training,
+                         float* total_ms, float* halo_ms) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    if (runs <= 0 || !total_ms || !halo_ms) return fail(-3, "absinthe_variant_run: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    RT(cudaSetDevice(v->device));
+    const size_t need = 1 + 2 * v->groups.size();
+    while (v->events.size() < need) {
+        cudaEvent_t e;
+        RT(cudaEventCreate(&e));
+        v->events.push_back(e);
+    }
+    for (int run = 0; run < 2 * runs; ++run) {
+        if (flush && (rc = absinthe_flush_l2(s))) return rc;
+        size_t ev = 0;
+        RT(cudaEventRecord(v->events[ev++], s));
+        for (Group& g : v->groups) {
+            if ((rc = launch_group(v, g, training != 0, s))) return rc;
+            RT(cudaEventRecord(v->events[ev++], s));
+            if (!training && (rc = halo_group(v, g, s))) return rc;
+            RT(cudaEventRecord(v->events[ev++], s));
+        }
+        RT(cudaStreamSynchronize(s));
+        if (run % 2 == 1) {
+            float total = 0.f, halo = 0.f;
+            RT(cudaEventElapsedTime(&total, v->events[0], v->events[ev - 1]));
+            for (size_t g = 0; g < v->groups.size(); ++g) {
+                float t = 0.f;
+                RT(cudaEventElapsedTime(&t, v->events[1 + 2 * g], v->events[2 + 2 * g]));
+                halo += t;
+            }
+            total_ms[run / 2] = total;
+            halo_ms[run / 2] = training ? 0.f : halo;
+        }
+    }
+    return 0;
+}
+
+int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inputs,
+                                double* const* h_outputs, void* stream) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t bytes = absinthe_variant_field_bytes(v);
+    for (size_t n = 0; n < v->inputs.size(); ++n)
+        RT(cudaMemcpyAsync(v->fields[v->inputs[n]].ptr, h_inputs[n], bytes, cudaMemcpyHostToDevice, s));
+    if ((rc = absinthe_variant_apply(v, s))) return rc;
+    for (size_t n = 0; n < v->outputs.size(); ++n)
+        RT(cudaMemcpyAsync(h_outputs[n], v->fields[v->outputs[n]].ptr, bytes, cudaMemcpyDeviceToHost, s));
+    RT(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int absinthe_make_periodic(double* d_field, int X, int Y, int Z, int HX, int HY, int HZ, void* stream) {
+    if (!d_field) return fail(-3, "absinthe_make_periodic: null field");
+    FieldList list{};
+    list.count = 1;
+    list.ptr[0] = d_field;
+    return periodic_update(list, Geometry{X, Y, Z, HX, HY, HZ}, 7, (cudaStream_t)stream);
+}
+
+int absinthe_make_periodic_ik(double* d_field, int X, int Y, int Z, int HX, int HY, int HZ, void* stream) {
+    if (!d_field) return fail(-3, "absinthe_make_periodic_ik: null field");
+    Geometry g{X, Y, Z, HX, HY, HZ};
+    if (!(g.X >= g.HX && g.Z >= g.HZ)) return fail(-3, "absinthe_make_periodic_ik: extent smaller than halo");
+    FieldList list{};
+    list.count = 1;
+    list.ptr[0] = d_field;
+    // i faces on interior rows, then k faces on full planes; j-halo rows are refreshed by the
+    // neighbour exchange afterwards (which carries their i and k halos with it)
+    long total = 2L * g.HZ * g.plane() + (long)g.Z * g.Y * 2 * g.HX;
+    periodic_kernel<<<launch_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(list, g, 5);
+    RT(cudaGetLastError());
+    return 0;
+}
+
+void absinthe_fill_rand(double* h_dst, size_t count, unsigned seed, int reseed) {
+    if (reseed) std::srand(seed);
+    for (size_t n = 0; n < count; ++n) h_dst[n] = std::rand();
+}
+
+int absinthe_halo_pack(const double* d_field, double* d_buffer, int X, int Y, int Z, int HX, int HY,
+                       int HZ, int j0, int width, void* stream) {
+    Geometry g{X, Y, Z, HX, HY, HZ};
+    long total = g.planes() * width * g.row();
+    pack_kernel<<<launch_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(d_field, d_buffer, g, j0, width, 0);
+    RT(cudaGetLastError());
+    return 0;
+}
+
+int absinthe_halo_unpack(double* d_field, const double* d_buffer, int X, int Y, int Z, int HX, int HY,
+                         int HZ, int j0, int width, void* stream) {
+    Geometry g{X, Y, Z, HX, HY, HZ};
+    long total = g.planes() * width * g.row();
+    pack_kernel<<<launch_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(d_field, const_cast<double*>(d_buffer), g, j0, width, 1);
+    RT(cudaGetLastError());
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,348 @@
+"""Kernel planning for the CUDA emitter.
+
+Takes an analysed program (``analysis.analyse``) and decides, for every fused
+group, everything ``template_tiling.cu`` needs to render one sm_100a kernel:
+
+* the reference's tile geometry -- tile size ``T = ceil(S/N)`` and centred,
+  truncating offset ``O = -(T*N - S)/2`` (ref template_tiling.cpp:228-233),
+  tiles enumerated x-fastest (ref :240-242).  One tile is one CTA's unit of
+  work; CTAs are persistent and take tiles ``blockIdx.x, +gridDim.x, ...``.
+* a *sub-tile* ``B <= T``: the box whose haloed inputs (two TMA stages) and
+  intermediates fit in shared memory.  A tile is walked as ``ceil(T/B)``
+  sub-tiles with overlapped (redundant) evaluation exactly like the tiles
+  themselves, so results do not depend on ``B``.
+* per input: the haloed box to stage (``LOOPS (+) OFFSETS`` of its consumers,
+  what the reference's analyzer calls ``accesses``, ref stencil_analyzer.py:137-142),
+  its shared-memory offset and strides, its tensor-map box.
+* per stencil ("pass"): the evaluation box (tile grown by ``LOOPS``), where
+  the result goes (shared-memory intermediate and/or global output) and the
+  stencil text with every ``field(i+a,j+b,k+c)`` access rewritten to an
+  indexed load -- the expression text between accesses is untouched, so
+  operand order is the reference's.
+
+The plan also yields the launcher descriptor (``descriptor_text``): fields,
+kernels, launch shapes, parameter-block layout, halo lists.
+"""
+
+from . import analysis as A
+
+SMEM_LIMIT = 227 * 1024          # opt-in maximum per CTA on sm_100a
+DEFAULTS = {
+    "THREADS": 256,
+    "STAGES": 2,
+    "SMEM_BUDGET": 110 * 1024,   # two CTAs per SM
+    "LOAD": "tma",               # "tma" | "ldg"
+    "SUBTILE": None,             # (BX, BY, BZ) override
+    "FMAD": False,               # False -> -fmad=false: bit-exact with the strict oracle
+    "FUSE_HALO": False,
+}
+MAX_BOX = 256                    # TMA box limit per dimension
+ALIGN_DOUBLES = 16               # 128-byte alignment of every staged box
+
+
+def c_trunc_div(a, b):
+    """C++ integer division (truncation toward zero) -- Python's // floors."""
+    q = abs(a) // abs(b)
+    return q if (a >= 0) == (b > 0) else -q
+
+
+def tile_geometry(size, count):
+    """(tile size, origin offset) of ``count`` tiles over ``size`` points (ref :228-233)."""
+    t = A.ceil_div(size, count)
+    return t, c_trunc_div(-(t * count - size), 2)
+
+
+def options(program):
+    opts = dict(DEFAULTS)
+    opts.update(program.get("CUDA", {}))
+    return opts
+
+
+def _round_up(value, multiple):
+    return (value + multiple - 1) // multiple * multiple
+
+
+def _splits(extent):
+    """Candidate sub-tile extents: even splits of ``extent`` into 1, 2, 3, ... parts."""
+    seen, out = set(), []
+    for parts in range(1, extent + 1):
+        b = A.ceil_div(extent, parts)
+        if b not in seen:
+            seen.add(b)
+            out.append(b)
+    return out
+
+
+class GroupPlan:
+    """Everything needed to render and launch the kernel of one fused group."""
+
+    def __init__(self, program, group, opts):
+        self.program, self.group, self.opts = program, group, opts
+        self.id = group["ID"] + 1          # kernel numbering follows the outer (schedule) id
+        self.stencils = group["STENCILS"]
+        self.names = [s["NAME"] for s in self.stencils]
+        dims = (program["X"], program["Y"], program["Z"])
+        self.S = dims
+        self.H = (program["HX"], program["HY"], program["HZ"])
+        self.N = (group["NX"], group["NY"], group["NZ"])
+        geo = [tile_geometry(s, n) for s, n in zip(dims, self.N)]
+        self.T = tuple(g[0] for g in geo)
+        self.O = tuple(g[1] for g in geo)
+        self.tiles = self.N[0] * self.N[1] * self.N[2]
+        self.reach = A.group_reach(group)
+        self.inputs = list(group["INPUTS"])
+        self.outputs = list(group["OUTPUTS"])
+        # a stencil result lives in shared memory when a later stencil of the group reads it
+        self.read_later = set()
+        for n, s in enumerate(self.stencils):
+            for field in s["OFFSETS"]:
+                if field in self.names[:n]:
+                    self.read_later.add(field)
+        self.row = dims[0] + 2 * self.H[0]
+        self.plane = self.row * (dims[1] + 2 * self.H[1])
+        self.load = opts["LOAD"]
+        if self.load == "tma" and (self.row % 2 or not self.inputs):
+            self.load = "ldg"              # TMA needs 16-byte global strides
+        self.stages = opts["STAGES"] if self.load == "tma" else 1
+        self.threads = opts["THREADS"]
+        self.B = self._choose_subtile()
+        self.nsub = tuple(A.ceil_div(t, b) for t, b in zip(self.T, self.B))
+        self._layout()
+
+    # -- shared-memory planning -----------------------------------------------------------
+    def _box_dims(self, B, box, even_x=False):
+        d = [B[a] + box[a][1] - box[a][0] for a in range(3)]
+        if even_x and d[0] % 2:
+            d[0] += 1
+        return d
+
+    def _footprint(self, B):
+        total = 0
+        for name in self.inputs:
+            d = self._box_dims(B, self.reach[name], even_x=True)
+            total += self.stages * _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+        for name in self.names:
+            if name in self.read_later:
+                d = self._box_dims(B, self.reach[name])
+                total += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+        return total * 8 + 64
+
+    def _cost(self, B):
+        moved = 0
+        for name in self.inputs:
+            d = self._box_dims(B, self.reach[name], even_x=True)
+            moved += d[0] * d[1] * d[2]
+        for s in self.stencils:
+            d = self._box_dims(B, self.reach[s["NAME"]])
+            moved += d[0] * d[1] * d[2] * len(s["OFFSETS"])
+        return moved / float(B[0] * B[1] * B[2])
+
+    def _choose_subtile(self):
+        if self.opts["SUBTILE"]:
+            B = tuple(min(b, t) for b, t in zip(self.opts["SUBTILE"], self.T))
+            assert self._footprint(B) <= SMEM_LIMIT, "SUBTILE does not fit in shared memory"
+            return B
+        widest = [0, 0, 0]
+        for name in self.inputs + self.names:
+            for a in range(3):
+                widest[a] = max(widest[a], self.reach[name][a][1] - self.reach[name][a][0])
+        budget = min(self.opts["SMEM_BUDGET"], SMEM_LIMIT)
+        best = None
+        for bx in _splits(self.T[0]):
+            if bx + widest[0] + 1 > MAX_BOX:
+                continue
+            for by in _splits(self.T[1]):
+                if by + widest[1] > MAX_BOX:
+                    continue
+                for bz in _splits(self.T[2]):
+                    if bz + widest[2] > MAX_BOX:
+                        continue
+                    B = (bx, by, bz)
+                    if self._footprint(B) > budget:
+                        continue
+                    key = (round(self._cost(B), 3), -bx * by * bz)
+                    if best is None or key < best[0]:
+                        best = (key, B)
+        if best is None:
+            B = (min(self.T[0], 32), 1, 1)
+            assert self._footprint(B) <= SMEM_LIMIT, "group does not fit in shared memory"
+            return B
+        return best[1]
+
+    def _layout(self):
+        B = self.B
+        cursor = 0
+        self.input_plan = []
+        for n, name in enumerate(self.inputs):
+            box = self.reach[name]
+            d = self._box_dims(B, box, even_x=True)
+            lo = [box[a][0] for a in range(3)]
+            self.input_plan.append({
+                "NAME": name, "INDEX": n, "LO": lo, "DIM": d, "OFFSET": cursor,
+                "ROW": d[0], "PLANE": d[0] * d[1], "CELLS": d[0] * d[1] * d[2],
+                # pointer bias so that relative (i, j, k) index the box directly
+                "BIAS": cursor - (lo[0] + lo[1] * d[0] + lo[2] * d[0] * d[1]),
+            })
+            cursor += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+        self.stage_doubles = cursor
+        self.stage_bytes = sum(p["CELLS"] for p in self.input_plan) * 8
+        cursor = self.stages * self.stage_doubles
+        self.temp_plan = {}
+        for name in self.names:
+            if name not in self.read_later:
+                continue
+            box = self.reach[name]
+            d = self._box_dims(B, box)
+            lo = [box[a][0] for a in range(3)]
+            self.temp_plan[name] = {
+                "NAME": name, "LO": lo, "DIM": d, "OFFSET": cursor, "ROW": d[0], "PLANE": d[0] * d[1],
+                "BIAS": cursor - (lo[0] + lo[1] * d[0] + lo[2] * d[0] * d[1]),
+            }
+            cursor += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+        self.barrier_offset = cursor * 8
+        self.smem_bytes = cursor * 8 + 8 * max(self.stages, 1) + 48
+        assert self.smem_bytes <= SMEM_LIMIT, "shared-memory plan exceeds the sm_100a limit"
+        # parameter block: tensor maps (128 B each, 64-byte aligned), pointers, tile control
+        off = 0
+        self.args = []
+        if self.load == "tma":
+            for p in self.input_plan:
+                self.args.append(("tmap", off, p["NAME"], p["DIM"]))
+                off += 128
+        self.in_ptr_offset = off
+        for name in self.inputs:
+            self.args.append(("ptr", off, name, None))
+            off += 8
+        if not self.inputs:
+            off += 8                        # the kernel declares at least one input slot
+        self.out_ptr_offset = off
+        for name in self.outputs:
+            self.args.append(("ptr", off, name, None))
+            off += 8
+        self.args.append(("tilectl", off, None, None))
+        off += 8
+        self.params_bytes = _round_up(off, 64)
+
+    # -- stencil text -----------------------------------------------------------------------
+    def _rewrite(self, code):
+        """Replace every access by an indexed load from its staged box / intermediate."""
+        inputs = {p["NAME"]: p for p in self.input_plan}
+
+        def access(match):
+            name = match.group(1)
+            off = [A._offset(match.group(n)) for n in (2, 3, 4)]
+            plan = inputs.get(name) or self.temp_plan.get(name)
+            assert plan is not None, "stencil reads unknown field " + name
+            terms = []
+            for sym, o, stride in zip("ijk", off, (1, plan["ROW"], plan["PLANE"])):
+                idx = sym if o == 0 else "(%s%+d)" % (sym, o)
+                terms.append(idx if stride == 1 else "%s*%d" % (idx, stride))
+            prefix = "in_" if name in inputs else "tmp_"
+            return "%s%s[%s]" % (prefix, name, " + ".join(terms))
+
+        return A._ACCESS.sub(access, code)
+
+    def passes(self):
+        out = []
+        pending = set()      # intermediates written since the last barrier
+        for s in self.stencils:
+            name = s["NAME"]
+            box = self.reach[name]
+            lo = [box[a][0] for a in range(3)]
+            hi = [box[a][1] for a in range(3)]
+            dim = self._box_dims(self.B, box)
+            reads_tmp = [f for f in s["OFFSETS"] if f in self.temp_plan]
+            sync_before = any(f in pending for f in reads_tmp)
+            if sync_before:
+                pending.clear()
+            to_smem = name in self.temp_plan
+            if to_smem:
+                pending.add(name)
+            out.append({
+                "NAME": name, "LO": lo, "HI": hi, "DIM": dim, "CELLS": dim[0] * dim[1] * dim[2],
+                "CODE": self._rewrite(s["LAMBDA"]), "SYNC_BEFORE": sync_before,
+                "TO_SMEM": to_smem, "TEMP": self.temp_plan.get(name),
+                "TO_GLOBAL": name in self.outputs,
+                "OUT_INDEX": self.outputs.index(name) if name in self.outputs else -1,
+                "READS_INPUTS": [f for f in s["OFFSETS"] if f in self.inputs],
+                "READS_TEMPS": reads_tmp,
+            })
+        return out
+
+    def context(self):
+        return {
+            "ID": self.id, "KERNEL": "absinthe_group%d" % self.id,
+            "THREADS": self.threads, "STAGES": self.stages, "TMA": self.load == "tma",
+            "T": self.T, "O": self.O, "N": self.N, "B": self.B, "NSUB": self.nsub,
+            "NSUB_TOTAL": self.nsub[0] * self.nsub[1] * self.nsub[2],
+            "TILES": self.tiles, "INPUTS": self.input_plan, "NIN": len(self.inputs),
+            "OUTPUTS": self.outputs, "NOUT": len(self.outputs),
+            "TEMPS": list(self.temp_plan.values()), "PASSES": self.passes(),
+            "STAGE_DOUBLES": self.stage_doubles, "STAGE_BYTES": self.stage_bytes,
+            "BARRIER_OFFSET": self.barrier_offset, "SMEM_BYTES": self.smem_bytes,
+            "PARAMS_BYTES": self.params_bytes, "NAMES": self.names,
+        }
+
+
+class Plan:
+    """Kernel plans of all fused groups of one analysed program."""
+
+    def __init__(self, program):
+        A.analyse(program)
+        self.program = program
+        self.opts = options(program)
+        self.groups = []
+        for outer in program["TILING"]["GROUPS"]:
+            if not outer["LOOPS"]:
+                continue                      # the dummy input-halo group
+            for inner in outer["GROUPS"]:
+                self.groups.append(GroupPlan(program, inner, self.opts))
+        tiling = program["TILING"]
+        self.inputs = sorted(tiling["INPUTS"])
+        self.outputs = sorted(tiling["OUTPUTS"])
+        produced = [n for g in self.groups for n in g.outputs]
+        self.temps = sorted(set(produced) - set(self.outputs))
+
+    def context(self):
+        p = self.program
+        ctx = {k: p[k] for k in ("X", "Y", "Z", "HX", "HY", "HZ")}
+        ctx.update(VARIANT=p.get("VARIANT", p.get("NAME", "")), GROUPS=[g.context() for g in self.groups],
+                   ANY_TMA=any(g.load == "tma" for g in self.groups), FMAD=self.opts["FMAD"])
+        return ctx
+
+    def nvcc_flags(self):
+        flags = ["-std=c++17", "-O3", "-lineinfo", "-gencode", "arch=compute_100a,code=sm_100a"]
+        if not self.opts["FMAD"]:
+            flags.append("-fmad=false")
+        return flags
+
+    def descriptor_text(self):
+        p = self.program
+        training = p.get("TRAINING", {})
+        lines = ["absinthe-variant 1", "name %s" % (p.get("VARIANT") or p.get("NAME") or "variant"),
+                 "# runs %d" % p.get("RUNS", 64), "# flush %d" % int(bool(p.get("FLUSH", True))),
+                 "# training %d" % int(bool(training)),
+                 "domain %d %d %d %d %d %d" % tuple(p[k] for k in ("X", "Y", "Z", "HX", "HY", "HZ"))]
+        for name in self.inputs:
+            lines.append("field %s in" % name)
+        for name in self.outputs:
+            lines.append("field %s out" % name)
+        for name in self.temps:
+            lines.append("field %s tmp" % name)
+        for g in self.groups:
+            lines.append("group %d kernel absinthe_group%d threads %d smem %d tiles %d params %d "
+                         "training_step %d fused_halo %d" % (
+                             g.id, g.id, g.threads, g.smem_bytes, g.tiles, g.params_bytes,
+                             training.get("STRIDE", 20), 0))
+            for kind, off, name, dim in g.args:
+                if kind == "tmap":
+                    lines.append("arg tmap %d %s %d %d %d" % (off, name, dim[0], dim[1], dim[2]))
+                elif kind == "ptr":
+                    lines.append("arg ptr %d %s" % (off, name))
+                else:
+                    lines.append("arg tilectl %d" % off)
+            for name in g.outputs:
+                lines.append("halo %s" % name)
+            lines.append("endgroup")
+        lines.append("end")
+        return "\n".join(lines) + "\n"

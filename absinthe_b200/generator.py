@@ -1,0 +1,187 @@
+"""The generator surface of the reference, retargeted at sm_100a.
+
+Same entry points and argument meaning as ``stencil_generator.py`` of the
+reference -- ``generate_code(template, name, program)`` (ref :41-59),
+``generate_makefile`` (:62-89), ``build_experiment`` (:92-94),
+``generate_script`` (:97-109), ``parse_results`` (:112-158), ``write_results``
+(:161-177) -- so the experiment drivers keep their ``-g/-b/-p/-f`` recipe:
+
+* ``generate_code("template_tiling.cu" | "template_training.cu", folder + name + ".cu", program)``
+  analyses the program *in place* (like the reference), renders the CUDA source and writes a
+  launcher descriptor ``<name>.desc`` beside it.
+* the Makefile compiles every ``<name>.cu`` to ``<name>.cubin`` with
+  ``nvcc -gencode arch=compute_100a,code=sm_100a -fmad=false``.
+* ``run.sh`` executes ``python -m absinthe_b200.runner <name>`` per experiment; the runner
+  prints the reference's stdout protocol, so ``parse_results`` / ``results.csv`` are unchanged.
+"""
+
+import csv
+import hashlib
+import os
+import subprocess
+import sys
+from collections import deque
+
+from jinja2 import Environment, FileSystemLoader
+
+from . import analysis as A
+from .emitter import Plan
+
+TEMPLATE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "templates")
+CACHE_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "build", "variants")
+CUDA_TEMPLATES = ("template_tiling.cu", "template_training.cu")
+
+TOTAL_PREFIX = "   - total time (min/median/max) [ms]: "
+HALO_PREFIX = "   - halo time (min/median/max) [ms]: "
+DOMAIN_PREFIX = "   - domain "
+VARIANT_PREFIX = "   - variant "
+
+
+def compute_schedule(program):
+    """PUT / WAIT / COMP entries in program order (ref stencil_generator.py:13-38).
+
+    A group's halo exchange is put right after its computation and awaited right before
+    the *next* group starts, which is where the multi-GPU driver overlaps it.
+    """
+    schedule = []
+    inflight = deque([None])
+    for group in program["TILING"]["GROUPS"]:
+        awaited = inflight.popleft()
+        if awaited:
+            schedule.append(awaited)
+        if group["LOOPS"]:
+            schedule.append({"TYPE": "COMP", "GROUP": group})
+        if group["HALOS"]:
+            schedule.append({"TYPE": "PUT", "GROUP": group})
+            inflight.append({"TYPE": "WAIT", "GROUP": group})
+        else:
+            inflight.append(None)
+    program["SCHEDULE"] = schedule
+
+
+def _environment():
+    # templates are looked up in the working directory first (the reference's convention,
+    # ref stencil_generator.py:54) and then in the package
+    return Environment(loader=FileSystemLoader([os.getcwd(), TEMPLATE_DIR]), keep_trailing_newline=True)
+
+
+def render(template, program):
+    """Analyse ``program`` in place and return (cuda source, descriptor text, nvcc flags)."""
+    if template not in CUDA_TEMPLATES:
+        raise ValueError("absinthe_b200 renders %s, not '%s' (the C++/OpenMP templates belong to the "
+                         "reference)" % (" / ".join(CUDA_TEMPLATES), template))
+    A.analyse(program)
+    if "SCHEDULE" not in program:
+        compute_schedule(program)
+    if template == "template_training.cu":
+        program.setdefault("TRAINING", {"STRIDE": 20})
+    plan = Plan(program)
+    context = plan.context()
+    context["TRAINING"] = template == "template_training.cu"
+    source = _environment().get_template("template_tiling.cu").render(context)
+    return source, plan.descriptor_text(), plan.nvcc_flags()
+
+
+def generate_code(template, name, program):
+    """Render ``program`` to ``name`` (a .cu path) and write ``<stem>.desc`` beside it."""
+    source, descriptor, flags = render(template, program)
+    stem = name[:-3] if name.endswith(".cu") else name
+    with open(stem + ".cu", "w") as handle:
+        handle.write(source)
+    with open(stem + ".desc", "w") as handle:
+        handle.write(descriptor)
+    program.setdefault("CUDA", {})["NVCC_FLAGS"] = flags
+
+
+def nvcc_command(flags, source, target):
+    return ["nvcc"] + list(flags) + ["-cubin", "-o", target, source]
+
+
+def generate_makefile(name, experiments):
+    """One ``<experiment>.cubin`` rule per experiment (ref stencil_generator.py:62-89)."""
+    strict = [e for e in experiments.values() if not e.get("CUDA", {}).get("FMAD", False)]
+    flags = ["-std=c++17", "-O3", "-lineinfo", "-gencode arch=compute_100a,code=sm_100a"]
+    if len(strict) == len(experiments):
+        flags.append("-fmad=false")
+    with open(name, "w", newline="\n") as handle:
+        handle.write("\nNVCC=nvcc\n")
+        handle.write("NVCCFLAGS= \\\n\t" + " \\\n\t".join(flags) + "\n\n")
+        handle.write("all: " + " ".join(key + ".cubin" for key in experiments) + "\n\n")
+        for key in experiments:
+            handle.write("%s.cubin: %s.cu\n" % (key, key))
+            handle.write("\t$(NVCC) $(NVCCFLAGS) -cubin -o $@ $<\n\n")
+        handle.write("clean:\n\trm -f *.cubin\n")
+
+
+def build_experiment(name):
+    """Build everything in the working directory, like the reference (ref :92-94)."""
+    subprocess.call(["make", "-j", str(os.cpu_count() or 1)])
+
+
+def generate_script(name, experiments, cores, runs):
+    """``run.sh``: one runner invocation per experiment and repetition (ref :97-109)."""
+    with open(name, "w", newline="\n") as handle:
+        handle.write("#!/bin/bash -l\n")
+        handle.write("# CORES in the variant description = %s SMs of the target GPU\n\n" % cores)
+        handle.write("export CUDA_DEVICE_MAX_CONNECTIONS=1\n\n")
+        for _ in range(runs):
+            for key in experiments:
+                handle.write("%s -m absinthe_b200.runner ./%s\n" % (os.path.basename(sys.executable), key))
+
+
+def parse_results(results, skip=16):
+    """stdout of a run -> rows ``[VAR, X, Y, Z, TOTAL, HALO]`` (ref stencil_generator.py:112-158).
+
+    A row is produced by every ``halo time`` line once ``skip`` samples of the current
+    binary (counted from its ``domain`` line) have been dropped.
+    """
+    rows, variant, domain, total, remaining = [], None, [], [], 0
+    with open(results, "r") as handle:
+        for line in handle:
+            if line.startswith(DOMAIN_PREFIX):
+                domain = [int(v) for v in line[len(DOMAIN_PREFIX):].split(", ")]
+                remaining = skip
+            elif line.startswith(VARIANT_PREFIX):
+                variant = line[len(VARIANT_PREFIX):].rstrip()
+            elif line.startswith(TOTAL_PREFIX):
+                total = [float(v) for v in line[len(TOTAL_PREFIX):].split("/")]
+            elif line.startswith(HALO_PREFIX):
+                halo = [float(v) for v in line[len(HALO_PREFIX):].split("/")]
+                if remaining == 0:
+                    rows.append([variant] + [str(v) for v in domain] + [str(v) for v in total]
+                                + [str(v) for v in halo])
+                remaining = max(0, remaining - 1)
+    return rows
+
+
+def write_results(rows, table):
+    """rows -> ``VAR,X,Y,Z,TOTAL,HALO`` csv (ref stencil_generator.py:161-177)."""
+    print("-> writing results to " + table)
+    with open(table, "w") as handle:
+        out = csv.writer(handle, delimiter=",", quotechar="'", lineterminator="\n")
+        out.writerow(["VAR", "X", "Y", "Z", "TOTAL", "HALO"])
+        for row in rows:
+            out.writerow(row)
+
+
+# ---------------------------------------------------------------------------------------
+# In-process build with a content-addressed cache (tests, bench, auto-tuner).
+# ---------------------------------------------------------------------------------------
+def build_variant(program, template="template_tiling.cu", cache_dir=None):
+    """Render + compile ``program``; returns (descriptor path, cubin path).  Cached by content."""
+    source, descriptor, flags = render(template, program)
+    tag = hashlib.sha256((source + descriptor + " ".join(flags)).encode()).hexdigest()[:24]
+    cache_dir = os.path.abspath(cache_dir or CACHE_DIR)
+    os.makedirs(cache_dir, exist_ok=True)
+    stem = os.path.join(cache_dir, tag)
+    if not (os.path.exists(stem + ".cubin") and os.path.exists(stem + ".desc")):
+        with open(stem + ".cu", "w") as handle:
+            handle.write(source)
+        tmp = "%s.%d.tmp" % (stem, os.getpid())
+        proc = subprocess.run(nvcc_command(flags, stem + ".cu", tmp), capture_output=True, text=True)
+        if proc.returncode != 0:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (stem + ".cu", proc.stderr[-4000:]))
+        os.replace(tmp, stem + ".cubin")
+        with open(stem + ".desc", "w") as handle:
+            handle.write(descriptor)
+    return stem + ".desc", stem + ".cubin"

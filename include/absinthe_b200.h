@@ -1,0 +1,132 @@
+/*
+ * absinthe_b200 -- C ABI of the B200 launcher for Absinthe's fused/tiled stencil sequences.
+ *
+ * The reference has no in-process FFI: its hot path is a generated stand-alone C++/OpenMP
+ * program per implementation variant (ref template_tiling.cpp:179-397), reached through
+ * source generation + process execution + stdout parsing.  This header
+ * is the boundary a maintainer binds instead (ctypes stub in INTEGRATION.md): the generated
+ * variant is no longer a program but a (descriptor, cubin) pair produced by
+ * generate_code("template_tiling.cu", ...), and the functions below replace the pieces of the
+ * reference's main():
+ *
+ *   absinthe_variant_load    <- the per-variant build (ref stencil_generator.py:62-94) + the tile /
+ *                               loop tables of main() (ref template_tiling.cpp:223-275)
+ *   absinthe_variant_bind    <- the array / view set-up (ref template_tiling.cpp:205-219)
+ *   absinthe_variant_apply   <- one pass of HOT LOOP 1 + HOT LOOP 2: every fused group's tile loop
+ *                               (ref template_tiling.cpp:301-336) followed by the periodic halo
+ *                               update of its outputs (ref :338-368)
+ *   absinthe_variant_run     <- the timing loop and its total / halo accumulators
+ *                               (ref template_tiling.cpp:285-376; training: template_training.cpp:259-319)
+ *   absinthe_make_periodic   <- make_periodic (ref template_tiling.cpp:136-159)
+ *   absinthe_fill_rand       <- array() initialisation from std::rand (ref template_tiling.cpp:62-64,209)
+ *   absinthe_flush_l2        <- the cache flush between runs (ref template_tiling.cpp:287-297)
+ *   absinthe_halo_pack/unpack<- the PUT / WAIT schedule slots the reference never filled in
+ *                               (ref stencil_generator.py:23-37), used by the multi-GPU decomposition
+ *
+ * Conventions: plain pointers and sizes only.  Every function returning int returns 0 on success
+ * and a non-zero CUDA / launcher error code otherwise; the message is available from
+ * absinthe_last_error() (thread-local).  Fields are fp64, laid out exactly like the reference's
+ * array<T,X,Y,Z> (ref template_tiling.cpp:59-79): (X+2HX)(Y+2HY)(Z+2HZ) doubles, i fastest, halos
+ * included, no padding.  Device buffers are owned by the caller; the library owns only the
+ * inter-group temporaries and scratch it allocates at load time.  One host thread drives one
+ * variant at a time; all work is enqueued on the caller's stream.  There is no CPU fallback.
+ */
+#ifndef ABSINTHE_B200_H
+#define ABSINTHE_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ABSINTHE_ABI_VERSION 1
+
+typedef struct absinthe_variant absinthe_variant;
+
+int absinthe_abi_version(void);
+const char* absinthe_last_error(void);
+
+/* number of CUDA devices visible, or a negative error code */
+int absinthe_device_count(void);
+
+/* ---- variant life cycle ------------------------------------------------------------------ */
+
+/* descriptor: NUL-terminated text written next to the .cu by generate_code (the .desc file);
+ * cubin: image compiled from the generated .cu for sm_100a. */
+int absinthe_variant_load(const char* descriptor, const void* cubin, size_t cubin_bytes,
+                          int device, absinthe_variant** out);
+void absinthe_variant_free(absinthe_variant* v);
+
+/* dims = {X, Y, Z, HX, HY, HZ} */
+int absinthe_variant_info(const absinthe_variant* v, int dims[6], int* n_inputs, int* n_outputs,
+                          int* n_groups);
+/* name of the idx-th program input (is_output == 0) or output (is_output != 0); order is the
+ * sorted order of TILING.INPUTS / TILING.OUTPUTS */
+const char* absinthe_variant_field(const absinthe_variant* v, int is_output, int idx);
+/* bytes of one field: (X+2HX)(Y+2HY)(Z+2HZ) * 8 */
+size_t absinthe_variant_field_bytes(const absinthe_variant* v);
+/* kernels launched by one absinthe_variant_apply (group kernels + halo kernels) */
+int absinthe_variant_launches(const absinthe_variant* v);
+/* 1 if the periodic update is fused into the group kernels (no separate halo kernels) */
+int absinthe_variant_fused_halo(const absinthe_variant* v);
+
+/* device pointers, inputs with periodic halos already applied */
+int absinthe_variant_bind(absinthe_variant* v, const double* const* d_inputs,
+                          double* const* d_outputs);
+
+/* ---- execution --------------------------------------------------------------------------- */
+
+/* one application of the whole sequence, asynchronous on `stream` (a cudaStream_t) */
+int absinthe_variant_apply(absinthe_variant* v, void* stream);
+/* the same captured once into a CUDA graph and replayed */
+int absinthe_variant_apply_graph(absinthe_variant* v, void* stream);
+/* only group `group` (1-based, as numbered by the analyzer); with_halo != 0 adds its halo update.
+ * Used by the multi-GPU driver to interleave halo exchanges between groups. */
+int absinthe_variant_apply_group(absinthe_variant* v, int group, int with_halo, void* stream);
+/* names of the outputs of `group` that need a halo update: returns count, names via idx */
+int absinthe_variant_group_outputs(const absinthe_variant* v, int group);
+const char* absinthe_variant_group_output(const absinthe_variant* v, int group, int idx);
+/* device pointer of any field of the variant (inputs, outputs, inter-group temporaries) */
+double* absinthe_variant_field_ptr(const absinthe_variant* v, const char* name);
+
+/* The reference's measurement loop: 2*runs applications, every odd one reported.
+ * total_ms[r] = group kernels + halo updates, halo_ms[r] = halo updates only (TOTAL includes HALO,
+ * ref template_tiling.cpp:368).  flush != 0 evicts L2 before every application (untimed).
+ * training != 0 runs the training protocol instead (one tile per SM, no halo update,
+ * ref template_training.cpp:276-311) and reports halo_ms = 0. */
+int absinthe_variant_run(absinthe_variant* v, void* stream, int runs, int flush, int training,
+                         float* total_ms, float* halo_ms);
+
+/* End-to-end with HOST buffers: H2D copy of every input, one application, D2H copy of every
+ * output, synchronised on return.  h_inputs must have periodic halos. */
+int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inputs,
+                                double* const* h_outputs, void* stream);
+
+/* ---- field helpers ----------------------------------------------------------------------- */
+
+/* periodic boundary condition on a device field (i, then j, then k faces; corners consistent) */
+int absinthe_make_periodic(double* d_field, int X, int Y, int Z, int HX, int HY, int HZ,
+                           void* stream);
+/* host: glibc srand(seed) when reseed != 0, then dst[n] = (double) rand() for n < count */
+void absinthe_fill_rand(double* h_dst, size_t count, unsigned seed, int reseed);
+/* write a buffer larger than L2 so the next kernel starts cold */
+int absinthe_flush_l2(void* stream);
+
+/* ---- multi-GPU halo faces (domain decomposed along j; rows are contiguous per k-plane) ---- */
+
+/* pack `width` rows starting at padded row `j0` of every k-plane into a dense buffer
+ * [planes][width][X+2HX]; unpack is the inverse.  planes = Z+2HZ. */
+int absinthe_halo_pack(const double* d_field, double* d_buffer, int X, int Y, int Z, int HX,
+                       int HY, int HZ, int j0, int width, void* stream);
+int absinthe_halo_unpack(double* d_field, const double* d_buffer, int X, int Y, int Z, int HX,
+                         int HY, int HZ, int j0, int width, void* stream);
+/* periodic update restricted to the i and k faces (the j faces come from the neighbour ranks) */
+int absinthe_make_periodic_ik(double* d_field, int X, int Y, int Z, int HX, int HY, int HZ,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* ABSINTHE_B200_H */
