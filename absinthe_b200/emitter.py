@@ -112,8 +112,11 @@ class GroupPlan:
     # -- shared-memory planning -----------------------------------------------------------
     def _box_dims(self, B, box, even_x=False):
         d = [B[a] + box[a][1] - box[a][0] for a in range(3)]
-        if even_x and d[0] % 2:
-            d[0] += 1
+        if even_x and self.load == "tma":
+            # TMA wants the box to start on a 16-byte boundary (an even fp64 column, measured:
+            # odd start columns raise "illegal instruction") and its inner extent to be a
+            # multiple of 16 bytes: load from the even column at or below the first one needed.
+            d[0] = d[0] + 1 + (d[0] + 1) % 2
         return d
 
     def _footprint(self, B):

@@ -1,0 +1,89 @@
+"""Host logic of the generator surface: rendering, descriptor, Makefile/run.sh, results parsing."""
+
+import json
+import os
+
+import pytest
+
+from absinthe_b200 import generator as G
+from absinthe_b200 import programs as P
+from absinthe_b200.emitter import Plan, SMEM_LIMIT
+from common import zoo
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_parse_results_matches_reference_rows():
+    want = json.load(open(os.path.join(GOLDEN, "parse_results.json")))
+    sample = os.path.join(GOLDEN, "sample_output.txt")
+    assert G.parse_results(sample, 0) == want["skip0"]
+    assert G.parse_results(sample, 1) == want["skip1"]
+    assert G.parse_results(sample) == want["skip16"]
+
+
+def test_write_results_format(tmp_path):
+    rows = G.parse_results(os.path.join(GOLDEN, "sample_output.txt"), 0)
+    table = tmp_path / "results.csv"
+    G.write_results(rows, str(table))
+    lines = table.read_text().split("\n")
+    assert lines[0] == "VAR,X,Y,Z,TOTAL,HALO"
+    assert lines[1] == "alpha,64,64,60,2.5,0.5"
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/diffusion"), reason="reference data not mounted")
+def test_parse_results_on_shipped_log():
+    import csv
+    rows = G.parse_results("/root/reference/diffusion/output.txt")
+    with open("/root/reference/diffusion/results.csv") as handle:
+        shipped = list(csv.reader(handle, quotechar="'"))[1:]
+    assert rows == shipped
+
+
+def test_generate_code_writes_source_and_descriptor(tmp_path):
+    program = P.make_program("fastwaves", variant="fw")
+    G.generate_code("template_tiling.cu", str(tmp_path / "fw.cu"), program)
+    source = (tmp_path / "fw.cu").read_text()
+    desc = (tmp_path / "fw.desc").read_text()
+    assert "absinthe_group1" in source and "cp.async.bulk.tensor.3d" in source
+    assert desc.startswith("absinthe-variant 1\nname fw\n")
+    assert "SCHEDULE" in program and [e["TYPE"] for e in program["SCHEDULE"]] == ["PUT", "WAIT", "COMP"]
+    with pytest.raises(ValueError):
+        G.generate_code("template_tiling.cpp", str(tmp_path / "x.cpp"), P.make_program("advection"))
+
+
+def test_stencil_text_is_pasted_with_only_accesses_rewritten():
+    import re
+    program = P.make_program("advection")
+    source, _, flags = G.render("template_tiling.cu", program)
+    assert "-fmad=false" in flags
+    strip = lambda s: re.sub(r"\s+", "", s)
+    for name, code in program["STENCILS"].items():
+        # rewriting accesses back to placeholders must give the original skeleton
+        skeleton = strip(re.sub(r"\w+\([^()]*\)", "@", code))
+        assert skeleton in strip(re.sub(r"(in|tmp)_\w+\[[^\[\]]*\]", "@", source)), name
+
+
+@pytest.mark.parametrize("name,program", zoo(), ids=[c[0] for c in zoo()])
+def test_plans_fit_shared_memory_and_cover_tiles(name, program):
+    plan = Plan(P.clone(program))
+    for g in plan.groups:
+        assert g.smem_bytes <= SMEM_LIMIT
+        for a in range(3):
+            assert g.B[a] <= g.T[a] and g.nsub[a] * g.B[a] >= g.T[a]
+            assert g.T[a] * g.N[a] >= g.S[a]                       # tiles cover the domain
+            assert g.O[a] <= 0 and g.T[a] * g.N[a] + g.O[a] >= g.S[a]
+        for p in g.input_plan:
+            assert max(p["DIM"]) <= 256                            # TMA box limit
+            if g.load == "tma":                                    # 16-byte inner extent, room for the
+                need = g.B[0] + g.reach[p["NAME"]][0][1] - g.reach[p["NAME"]][0][0]
+                assert p["DIM"][0] % 2 == 0 and p["DIM"][0] >= need + 1   # even-column start shift
+
+
+def test_makefile_and_script(tmp_path):
+    experiments = {"a": P.make_program("advection"), "b": P.make_program("diffusion")}
+    G.generate_makefile(str(tmp_path / "Makefile"), experiments)
+    G.generate_script(str(tmp_path / "run.sh"), experiments, 148, 2)
+    make = (tmp_path / "Makefile").read_text()
+    assert "a.cubin: a.cu" in make and "arch=compute_100a,code=sm_100a" in make and "-fmad=false" in make
+    script = (tmp_path / "run.sh").read_text().split("\n")
+    assert sum("absinthe_b200.runner ./a" in line for line in script) == 2
