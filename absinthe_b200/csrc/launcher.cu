@@ -530,6 +530,7 @@ void absinthe_variant_free(absinthe_variant* v) {
     if (!v) return;
     cudaSetDevice(v->device);
     if (v->graph) cudaGraphExecDestroy(v->graph);
+    if (v->graph_stream) cudaStreamDestroy(v->graph_stream);
     for (cudaEvent_t e : v->events) cudaEventDestroy(e);
     for (Field& f : v->fields)
         if (f.owned && f.ptr) cudaFree(f.ptr);
@@ -619,18 +620,19 @@ int absinthe_variant_apply_graph(absinthe_variant* v, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!v->graph || v->graph_stream != s) {
-        if (v->graph) { cudaGraphExecDestroy(v->graph); v->graph = nullptr; }
+    if (!v->graph) {
+        // capture on a private stream (the legacy default stream cannot be captured); the
+        // instantiated graph is then launched into whatever stream the caller passes
+        if (!v->graph_stream) RT(cudaStreamCreateWithFlags(&v->graph_stream, cudaStreamNonBlocking));
         cudaGraph_t graph = nullptr;
-        RT(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-        rc = absinthe_variant_apply(v, s);
-        cudaError_t e = cudaStreamEndCapture(s, &graph);
+        RT(cudaStreamBeginCapture(v->graph_stream, cudaStreamCaptureModeThreadLocal));
+        rc = absinthe_variant_apply(v, v->graph_stream);
+        cudaError_t e = cudaStreamEndCapture(v->graph_stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail((int)e, "cudaStreamEndCapture: %s", cudaGetErrorString(e));
         e = cudaGraphInstantiate(&v->graph, graph, 0);
         cudaGraphDestroy(graph);
         if (e != cudaSuccess) return fail((int)e, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
-        v->graph_stream = s;
     }
     RT(cudaGraphLaunch(v->graph, s));
     return 0;
@@ -644,6 +646,14 @@ int absinthe_variant_apply_group(absinthe_variant* v, int group, int with_halo, 
             if ((rc = launch_group(v, g, false, (cudaStream_t)stream))) return rc;
             return with_halo ? halo_group(v, g, (cudaStream_t)stream) : 0;
         }
+    return fail(-3, "variant '%s' has no group %d", v->name.c_str(), group);
+}
+
+int absinthe_variant_halo_group(absinthe_variant* v, int group, void* stream) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    for (Group& g : v->groups)
+        if (g.id == group) return halo_group(v, g, (cudaStream_t)stream);
     return fail(-3, "variant '%s' has no group %d", v->name.c_str(), group);
 }
 

@@ -1,0 +1,96 @@
+"""Horizontal domain decomposition across the GPUs of one box: j-slabs with NVLink halo exchange.
+
+The reference never filled in its distributed hooks -- ``TILING.NX/NY/NZ`` with
+``index[] = {0,0,0}`` (ref template_tiling.cpp:189-203), per-group ``HALOS`` and the ``PUT``/``WAIT``
+schedule slots (ref stencil_generator.py:23-37).  Here they mean: rank ``r`` of ``N`` owns the j-slab
+``[r*Y, (r+1)*Y)`` of a global ``X x (N*Y) x Z`` periodic domain (k stays whole, i-rows stay
+contiguous).  After a group's kernel, each of its outputs gets
+
+1. the local periodic update of its i and k faces (``absinthe_make_periodic_ik``),
+2. a PUT of its first / last ``HY`` interior rows -- every plane, full padded width, so the
+   neighbours also receive consistent i/k halos -- to ranks ``r-1`` / ``r+1`` (mod N), and
+3. a WAIT + unpack of the rows the neighbours put into its low / high j-halo.
+
+At N = 1 both neighbours are the rank itself and the result is exactly ``make_periodic``.
+Faces are packed by a kernel of the launcher into one contiguous buffer per direction (all outputs
+of the group together) and moved with ``torch.distributed`` P2P (NCCL over NVLink on the GPUs,
+gloo in the CPU tests of the protocol).
+"""
+
+
+def neighbours(rank, world):
+    """(previous, next) rank along j with periodic wrap."""
+    return (rank - 1) % world, (rank + 1) % world
+
+
+def face_rows(Y, HY):
+    """Padded row ranges: (low interior, high interior, low halo, high halo), each ``(j0, width)``."""
+    return (HY, HY), (Y, HY), (0, HY), (Y + HY, HY)
+
+
+class SlabExchange:
+    """Halo exchange of one variant's group outputs between the j-neighbour ranks."""
+
+    def __init__(self, variant, world, rank, process_group=None):
+        self.v, self.world, self.rank, self.pg = variant, world, rank, process_group
+        self.prev, self.next = neighbours(rank, world)
+        self.dims = (variant.X, variant.Y, variant.Z, variant.HX, variant.HY, variant.HZ)
+        self.buffers = {}
+
+    # -- device plumbing (overridden by the CPU protocol test) ----------------------------
+    def field_names(self, group):
+        return self.v.group_outputs(group)
+
+    def allocate(self, count):
+        import torch
+        X, Y, Z, HX, HY, HZ = self.dims
+        shape = (count, Z + 2 * HZ, HY, X + 2 * HX)
+        dev = "cuda:%d" % self.v.device
+        return [torch.empty(shape, dtype=torch.float64, device=dev) for _ in range(4)]
+
+    def local_faces(self, name):
+        from .launcher import check, load_library, _stream_handle
+        lib = load_library()
+        check(lib, lib.absinthe_make_periodic_ik(self.v.field_ptr(name), *self.dims, _stream_handle(None)),
+              "absinthe_make_periodic_ik")
+
+    def pack(self, name, buffer, j0, width):
+        from .launcher import check, load_library, _stream_handle
+        lib = load_library()
+        check(lib, lib.absinthe_halo_pack(self.v.field_ptr(name), buffer.data_ptr(), *self.dims, j0, width,
+                                          _stream_handle(None)), "absinthe_halo_pack")
+
+    def unpack(self, name, buffer, j0, width):
+        from .launcher import check, load_library, _stream_handle
+        lib = load_library()
+        check(lib, lib.absinthe_halo_unpack(self.v.field_ptr(name), buffer.data_ptr(), *self.dims, j0, width,
+                                            _stream_handle(None)), "absinthe_halo_unpack")
+
+    # -- protocol ---------------------------------------------------------------------------
+    def update(self, group):
+        """PUT + WAIT of every output of ``group`` (the slot after its COMP in the schedule)."""
+        import torch.distributed as dist
+        names = self.field_names(group)
+        if not names:
+            return
+        if group not in self.buffers:
+            self.buffers[group] = self.allocate(len(names))
+        send_low, send_high, recv_low, recv_high = self.buffers[group]
+        low_int, high_int, low_halo, high_halo = face_rows(self.dims[1], self.dims[4])
+        for n, name in enumerate(names):
+            self.local_faces(name)
+            self.pack(name, send_low[n], *low_int)
+            self.pack(name, send_high[n], *high_int)
+        if self.world == 1:
+            recv_high.copy_(send_low)
+            recv_low.copy_(send_high)
+        else:
+            ops = [dist.P2POp(dist.isend, send_low, self.prev, self.pg),
+                   dist.P2POp(dist.isend, send_high, self.next, self.pg),
+                   dist.P2POp(dist.irecv, recv_high, self.next, self.pg),
+                   dist.P2POp(dist.irecv, recv_low, self.prev, self.pg)]
+            for work in dist.batch_isend_irecv(ops):
+                work.wait()
+        for n, name in enumerate(names):
+            self.unpack(name, recv_low[n], *low_halo)
+            self.unpack(name, recv_high[n], *high_halo)

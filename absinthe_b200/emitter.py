@@ -131,13 +131,17 @@ class GroupPlan:
         return total * 8 + 64
 
     def _cost(self, B):
-        moved = 0
+        """Work per useful point of a sub-tile ``B``: staged cells (short rows cost extra: every
+        row pays about a sector and a half of slack), evaluated cells weighted by their operand
+        count, and a fixed price per work item (barriers, pipeline bubble)."""
+        row_slack, item_overhead = 12, 3000
+        moved = item_overhead
         for name in self.inputs:
             d = self._box_dims(B, self.reach[name], even_x=True)
-            moved += d[0] * d[1] * d[2]
+            moved += (d[0] + row_slack) * d[1] * d[2]
         for s in self.stencils:
             d = self._box_dims(B, self.reach[s["NAME"]])
-            moved += d[0] * d[1] * d[2] * len(s["OFFSETS"])
+            moved += d[0] * d[1] * d[2] * 0.25 * len(s["OFFSETS"])
         return moved / float(B[0] * B[1] * B[2])
 
     def _choose_subtile(self):

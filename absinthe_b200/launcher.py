@@ -21,7 +21,8 @@ SYMBOLS = [
     "absinthe_variant_load", "absinthe_variant_free", "absinthe_variant_info",
     "absinthe_variant_field", "absinthe_variant_field_bytes", "absinthe_variant_launches",
     "absinthe_variant_fused_halo", "absinthe_variant_bind", "absinthe_variant_apply",
-    "absinthe_variant_apply_graph", "absinthe_variant_apply_group", "absinthe_variant_group_outputs",
+    "absinthe_variant_apply_graph", "absinthe_variant_apply_group", "absinthe_variant_halo_group",
+    "absinthe_variant_group_outputs",
     "absinthe_variant_group_output", "absinthe_variant_field_ptr", "absinthe_variant_run",
     "absinthe_variant_apply_host", "absinthe_make_periodic", "absinthe_fill_rand", "absinthe_flush_l2",
     "absinthe_halo_pack", "absinthe_halo_unpack", "absinthe_make_periodic_ik",
@@ -60,6 +61,7 @@ def load_library(path=None):
     lib.absinthe_variant_apply.argtypes = [c.c_void_p, c.c_void_p]
     lib.absinthe_variant_apply_graph.argtypes = [c.c_void_p, c.c_void_p]
     lib.absinthe_variant_apply_group.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p]
+    lib.absinthe_variant_halo_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p]
     lib.absinthe_variant_group_outputs.argtypes = [c.c_void_p, c.c_int]
     lib.absinthe_variant_group_output.argtypes = [c.c_void_p, c.c_int, c.c_int]
     lib.absinthe_variant_group_output.restype = c.c_char_p
@@ -178,6 +180,10 @@ class Variant:
     def apply_group(self, group, with_halo=True, stream=None):
         check(self.lib, self.lib.absinthe_variant_apply_group(self.handle, group, int(with_halo),
                                                               _stream_handle(stream)), "apply_group")
+
+    def halo_group(self, group, stream=None):
+        check(self.lib, self.lib.absinthe_variant_halo_group(self.handle, group, _stream_handle(stream)),
+              "halo_group")
 
     def group_outputs(self, group):
         n = self.lib.absinthe_variant_group_outputs(self.handle, group)

@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: fused stencil sequences on a large synthetic domain.
+
+``python bench.py --gpus N --steps K --warmup W`` -- one rank per GPU (torchrun for N > 1).
+A *step* is one pass of the diffusion sequence and one pass of the fast-waves sequence
+(BASELINE.json configs[4]) over a 1024 x 1024 x 80 domain per GPU, each executed as its tuned
+fused/tiled variant through the C-ABI launcher, periodic halo updates included.  Printed metric:
+Mpoints/s, a point being one grid point taken through one whole sequence.
+
+``--impl reference`` times the reference's own OpenMP build (oracle/_ref, built in the
+development container) of the same variants on the host cores, on a bounded slab of the domain.
+"""
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+DOMAIN = (1024, 1024, 80)
+CPU_SLAB = (1024, 1024, 8)          # bounded sample for the CPU arms (same per-point work)
+TUNED = os.path.join(ROOT, "absinthe_b200", "tuned.json")
+TRAFFIC = os.path.join(ROOT, "profiles", "traffic.json")
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+
+
+def workload_programs(domain=DOMAIN):
+    """The two variants of the step: (name, program) with tuned groupings / tile counts."""
+    from absinthe_b200 import programs as P
+    tuned = {}
+    if os.path.exists(TUNED):
+        tuned = json.load(open(TUNED))
+    out = []
+    for kernel in ("diffusion", "fastwaves"):
+        seq = P.KERNELS[kernel][1]()
+        cfg = tuned.get(kernel, DEFAULT_VARIANTS[kernel])
+        groups = P.split_sequence(seq, cfg["assignment"])
+        program = P.make_program(kernel, groups, [tuple(t) for t in cfg["tiles"]], domain=domain,
+                                 variant="%s-%s" % (kernel, "-".join(str(a) for a in cfg["assignment"])))
+        if cfg.get("cuda"):
+            program["CUDA"] = dict(cfg["cuda"])
+        out.append((kernel, program))
+    return out
+
+
+# untuned fall-backs: diffusion one group per field, fast waves the HAND/AUTO two-group split
+DEFAULT_VARIANTS = {
+    "diffusion": {"assignment": [0] * 4 + [1] * 4 + [2] * 4 + [3] * 4, "tiles": [[8, 64, 80]] * 4},
+    "fastwaves": {"assignment": [0] * 6 + [1] * 3, "tiles": [[8, 64, 10]] * 2},
+}
+
+
+def scale_tiles(program, domain):
+    """The same tile *shapes* on another domain (tile counts follow the extents)."""
+    from absinthe_b200 import programs as P
+    from absinthe_b200.analysis import ceil_div
+    q = P.clone(program)
+    old = (q["X"], q["Y"], q["Z"])
+    q["X"], q["Y"], q["Z"] = domain
+    for outer in q["TILING"]["GROUPS"]:
+        for inner in outer["GROUPS"]:
+            for dim, o, n in zip("XYZ", old, domain):
+                shape = ceil_div(o, inner["N" + dim])
+                inner["N" + dim] = max(1, ceil_div(n, shape))
+    return q
+
+
+def prebuild():
+    """Compile everything the default run needs (called from __graft_entry__.build)."""
+    from absinthe_b200.generator import build_variant
+    from absinthe_b200 import programs as P
+    for _, program in workload_programs():
+        build_variant(P.clone(program))
+    try:
+        from oracle import build_ref
+        if build_ref.available():
+            for name, program in workload_programs():
+                slab = scale_tiles(program, CPU_SLAB)
+                slab["RUNS"] = 6
+                slab["VARIANT"] = program["VARIANT"]
+                build_ref.build_binary(slab, "bench_" + name)
+    except Exception as exc:
+        print("reference build skipped:", exc)
+
+
+# ---------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm, reasons, sm_max = [], set(), None
+        for row in self.rows:
+            try:
+                sm.append(float(row[0]))
+                sm_max = float(row[1])
+            except (ValueError, IndexError):
+                continue
+            for name, cell in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                  row[3:7]):
+                if cell == "Active":
+                    reasons.add(name)
+        busy = [c for c in sm if sm_max and c > 0.3 * sm_max] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": sm_max,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_time(name, steps, warmup):
+    """Run the prebuilt reference binary of ``name``; returns (median total ms, samples, threads)."""
+    exe = os.path.join(REF_DIR, "bench_" + name)
+    if not os.path.exists(exe):
+        return None
+    threads = os.cpu_count() or 1
+    env = dict(os.environ, OMP_PLACES="cores", OMP_PROC_BIND="close", OMP_NUM_THREADS=str(threads),
+               OMP_STACKSIZE="512M")
+    proc = subprocess.run("ulimit -s unlimited; exec " + exe, shell=True, env=env, capture_output=True, text=True,
+                          timeout=900)
+    totals = [float(line.split(":")[1]) for line in proc.stdout.splitlines()
+              if line.startswith("   - total time")]
+    if not totals:
+        return None
+    used = totals[min(warmup, len(totals) - 1):][:max(1, steps)]
+    return statistics.median(used), len(used), threads
+
+
+def cpu_port_time(name, program):
+    """Fallback CPU baseline: the sequential oracle restatement on one core."""
+    from oracle.reference_oracle import Oracle
+    import numpy as np
+    oracle = Oracle(program, fast_math=True)
+    rng = np.random.default_rng(0)
+    inputs = [oracle.make_periodic(rng.uniform(0.5, 1.5, oracle.shape)) for _ in oracle.inputs]
+    t0 = time.perf_counter()
+    oracle.run(inputs)
+    return (time.perf_counter() - t0) * 1e3
+
+
+def cpu_baseline(steps=3, warmup=1):
+    """Mpoints/s of the CPU arm on the bounded slab; prefers the real reference build."""
+    from absinthe_b200 import programs as P
+    points = CPU_SLAB[0] * CPU_SLAB[1] * CPU_SLAB[2]
+    total_ms, kind, threads, detail = 0.0, "reference", 1, {}
+    for name, program in workload_programs():
+        got = cpu_reference_time(name, steps, warmup)
+        if got is None:
+            kind = "port"
+            break
+        total_ms += got[0]
+        threads = got[2]
+        detail[name] = got[0]
+    if kind == "port":
+        total_ms, threads, detail = 0.0, 1, {}
+        small = (256, 256, 8)
+        points = small[0] * small[1] * small[2]
+        for name, program in workload_programs():
+            ms = cpu_port_time(name, scale_tiles(program, small))
+            total_ms += ms
+            detail[name] = ms
+        sample = "sequential oracle port, %dx%dx%d slab, one pass per sequence" % small
+    else:
+        sample = ("reference OpenMP build (g++ -O3 -ffast-math -fopenmp) of the same variants on a "
+                  "%dx%dx%d slab, median of %d timed runs per sequence" % (CPU_SLAB + (steps,)))
+    value = 2 * points / (total_ms * 1e-3) / 1e6
+    return {"value": value, "unit": "Mpoints/s", "cores": threads, "kind": kind, "sample": sample,
+            "ms_per_sequence": detail}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    base = cpu_baseline(steps=args.steps, warmup=args.warmup)
+    points = CPU_SLAB[0] * CPU_SLAB[1] * CPU_SLAB[2]
+    line = {
+        "impl": "reference", "metric": "fused_sequence_throughput", "value": base["value"], "unit": "Mpoints/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 2 * points / base["value"] / 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus), "cpu_baseline": base,
+        "e2e": {"value": base["value"], "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_config(gpus):
+    return {"workload": "diffusion+fastwaves fused sequences, %dx%dx%d fp64 per GPU, halo 3, periodic" % DOMAIN,
+            "domain_per_gpu": list(DOMAIN), "decomposition": "j-slabs x%d" % gpus,
+            "l2": "inputs (>6 GB per sequence) exceed the 126 MB L2; no flush needed between steps"}
+
+
+# ---------------------------------------------------------------------------------------
+def run_gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+    from absinthe_b200 import programs as P
+    from absinthe_b200.analysis import algorithmic_bytes_per_point
+    from absinthe_b200.build import build_launcher
+    from absinthe_b200.launcher import Variant, make_periodic
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    if local == 0:
+        build_launcher()
+    if world > 1:
+        dist.barrier()
+
+    from absinthe_b200.distributed import SlabExchange
+    variants = []
+    gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
+    for name, program in workload_programs():
+        v = Variant.from_program(P.clone(program), device=local)
+        dims = (v.X, v.Y, v.Z, v.HX, v.HY, v.HZ)
+        ins = []
+        for _ in v.inputs:
+            t = torch.rand(v.shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+            make_periodic(t, dims)
+            ins.append(t)
+        outs = [v.empty_field() for _ in v.outputs]
+        v.bind(ins, outs)
+        exchange = SlabExchange(v, world, rank) if world > 1 else None
+        analysed = P.clone(program)
+        from absinthe_b200.analysis import analyse
+        analyse(analysed)
+        groups = [g for o in analysed["TILING"]["GROUPS"] for g in o["GROUPS"]]
+        variants.append({"name": name, "v": v, "ins": ins, "outs": outs, "exchange": exchange,
+                         "bytes_per_point": algorithmic_bytes_per_point(analysed),
+                         "group_bytes": [8 * (len(g["INPUTS"]) + len(g["OUTPUTS"])) for g in groups],
+                         "group_names": ["%s:g%d(%s..%s)" % (name, n + 1, g["STENCILS"][0]["NAME"],
+                                                             g["STENCILS"][-1]["NAME"]) for n, g in enumerate(groups)]})
+    points = DOMAIN[0] * DOMAIN[1] * DOMAIN[2]
+
+    def step(record=None):
+        for item in variants:
+            v = item["v"]
+            for g in range(1, v.n_groups + 1):
+                if record is not None:
+                    a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    a.record()
+                    v.apply_group(g, with_halo=False)
+                    b.record()
+                else:
+                    v.apply_group(g, with_halo=False)
+                if item["exchange"] is not None:
+                    item["exchange"].update(g)
+                else:
+                    v.halo_group(g)
+                if record is not None:
+                    c.record()
+                    record.append((item["name"], g, a, b, c))
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    records = []
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for _ in range(args.steps):
+        step(records)
+    stop.record()
+    torch.cuda.synchronize()
+    elapsed_ms = start.elapsed_time(stop)
+    clocks = sampler.stop()
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    ms_per_step = elapsed_ms / args.steps
+    value = 2 * points * world / (ms_per_step * 1e-3) / 1e6
+
+    # per-kernel durations from the events of the timed region
+    kernel_ms, halo_ms = {}, {}
+    for name, g, a, b, c in records:
+        kernel_ms.setdefault((name, g), []).append(a.elapsed_time(b))
+        halo_ms.setdefault((name, g), []).append(b.elapsed_time(c))
+    breakdown = {}
+    dominant = None
+    for item in variants:
+        for g in range(1, item["v"].n_groups + 1):
+            k = statistics.mean(kernel_ms[(item["name"], g)])
+            h = statistics.mean(halo_ms[(item["name"], g)])
+            gbs = item["group_bytes"][g - 1] * points / (k * 1e-3) / 1e9
+            label = item["group_names"][g - 1]
+            breakdown[label] = {"kernel_ms": round(k, 4), "halo_ms": round(h, 4), "GBps": round(gbs, 1),
+                                "bytes_per_point": item["group_bytes"][g - 1]}
+            if dominant is None or k > dominant[1]:
+                dominant = (label, k, gbs)
+    peaks = {}
+    if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")):
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    peak, peak_kind = (peaks["hbm_gbs"], "measured copy bandwidth (MEASURED_PEAKS.json)") if "hbm_gbs" in peaks \
+        else (6650.0, "fallback of B200_PROFILING.md")
+    traffic = None
+    if os.path.exists(TRAFFIC):
+        traffic = json.load(open(TRAFFIC)).get(dominant[0])
+    step_bytes = sum(item["bytes_per_point"] for item in variants) * points
+    roofline = {"bound": "hbm", "kernel": dominant[0], "achieved": round(dominant[2], 1), "peak": peak,
+                "unit": "GB/s", "frac": round(dominant[2] / peak, 4), "traffic": traffic, "peak_kind": peak_kind,
+                "step_GBps": round(step_bytes * world / (ms_per_step * 1e-3) / 1e9, 1),
+                "step_frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
+                "frac_of_8TBps": round(dominant[2] / 8000.0, 4)}
+
+    # end to end through the public API with HOST buffers (pinned), copies inside the timed region
+    e2e = None
+    launches = sum(item["v"].launches for item in variants) * args.steps
+    if world == 1 or True:
+        e2e_steps = max(1, min(args.steps, 3))
+        host = []
+        for item in variants:
+            v = item["v"]
+            hin = [t.cpu().pin_memory() for t in item["ins"]]
+            hout = [torch.empty(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
+            host.append((v, hin, hout))
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            for v, hin, hout in host:
+                v.apply_host(hin, hout)
+        torch.cuda.synchronize()
+        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        if world > 1:
+            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_ms = float(t.item())
+        h2d = sum(len(hin) for _, hin, _ in host) * host[0][0].field_bytes
+        d2h = sum(len(hout) for _, _, hout in host) * host[0][0].field_bytes
+        e2e = {"value": round(2 * points * world / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpoints/s",
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 2),
+               "steps": e2e_steps, "api": "Variant.apply_host (absinthe_variant_apply_host)"}
+
+    if rank == 0:
+        line = {
+            "metric": "fused_sequence_throughput", "value": round(value, 1), "unit": "Mpoints/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
+            "gpu_launches": launches, "roofline": roofline, "breakdown": breakdown,
+            "variants": {item["name"]: workload_programs()[n][1]["VARIANT"] for n, item in enumerate(variants)},
+        }
+        if world == 1 and not args.no_cpu:
+            try:
+                line["cpu_baseline"] = cpu_baseline()
+            except Exception as exc:
+                line["cpu_baseline"] = {"error": str(exc)[:200]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    parser = argparse.ArgumentParser()
+    parser.add_argument("--gpus", type=int, default=1)
+    parser.add_argument("--steps", type=int, default=20)
+    parser.add_argument("--warmup", type=int, default=3)
+    parser.add_argument("--impl", default="absinthe_b200", choices=["absinthe_b200", "reference"])
+    parser.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = parser.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

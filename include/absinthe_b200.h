@@ -84,6 +84,8 @@ int absinthe_variant_apply_graph(absinthe_variant* v, void* stream);
 /* only group `group` (1-based, as numbered by the analyzer); with_halo != 0 adds its halo update.
  * Used by the multi-GPU driver to interleave halo exchanges between groups. */
 int absinthe_variant_apply_group(absinthe_variant* v, int group, int with_halo, void* stream);
+/* only the periodic halo update of the outputs of `group` */
+int absinthe_variant_halo_group(absinthe_variant* v, int group, void* stream);
 /* names of the outputs of `group` that need a halo update: returns count, names via idx */
 int absinthe_variant_group_outputs(const absinthe_variant* v, int group);
 const char* absinthe_variant_group_output(const absinthe_variant* v, int group, int idx);

@@ -1,0 +1,135 @@
+#!/usr/bin/env python
+"""Brute-force tile / launch-shape search on the GPU (the backend's version of the drivers' ``-a``).
+
+For one kernel and one fusion grouping, time every candidate (tile shape x CUDA options) on the
+large domain with the launcher's measurement loop and report Mpoints/s and effective GB/s.  The
+best candidate per kernel can be written to ``absinthe_b200/tuned.json`` (what bench.py runs).
+
+    python tools/autotune.py --kernel diffusion --assignment 0000111122223333 \
+        --tiles 128x16x1,128x8x1,256x8x1 --budgets 110,220 --threads 256,512 --out gpurun_out/tune.json
+"""
+
+import argparse
+import itertools
+import json
+import os
+import statistics
+import sys
+from concurrent.futures import ProcessPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+
+def make(kernel, assignment, shape, domain, cuda):
+    from absinthe_b200 import programs as P
+    from absinthe_b200.analysis import ceil_div
+    seq = P.KERNELS[kernel][1]()
+    groups = P.split_sequence(seq, assignment)
+    counts = tuple(max(1, ceil_div(d, s)) for d, s in zip(domain, shape))
+    program = P.make_program(kernel, groups, [counts] * len(groups), domain=domain,
+                             variant="%s-%s" % (kernel, "x".join(map(str, shape))))
+    program["CUDA"] = dict(cuda)
+    return program
+
+
+def compile_one(args):
+    from absinthe_b200.generator import build_variant
+    try:
+        return build_variant(make(*args)), None
+    except Exception as exc:      # a candidate that does not fit is simply skipped
+        return None, str(exc)[-300:]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kernel", required=True)
+    ap.add_argument("--assignment", required=True, help="group index per stencil, e.g. 0000111122223333")
+    ap.add_argument("--tiles", required=True, help="comma list of tile shapes TXxTYxTZ")
+    ap.add_argument("--domain", default="1024x1024x80")
+    ap.add_argument("--budgets", default="110", help="shared-memory budgets per CTA in KiB")
+    ap.add_argument("--threads", default="256")
+    ap.add_argument("--stages", default="2")
+    ap.add_argument("--loads", default="tma")
+    ap.add_argument("--subtiles", default="", help="optional comma list of BXxBYxBZ overrides")
+    ap.add_argument("--extra", default="", help="JSON dict merged into every candidate's CUDA options")
+    ap.add_argument("--runs", type=int, default=4)
+    ap.add_argument("--out", default="")
+    ap.add_argument("--save", action="store_true", help="write the winner into absinthe_b200/tuned.json")
+    args = ap.parse_args()
+
+    import torch
+    from absinthe_b200 import programs as P
+    from absinthe_b200.analysis import algorithmic_bytes_per_point, analyse
+    from absinthe_b200.build import build_launcher
+    from absinthe_b200.launcher import Variant, make_periodic
+    build_launcher()
+
+    domain = tuple(int(v) for v in args.domain.split("x"))
+    assignment = [int(c) for c in args.assignment]
+    shapes = [tuple(int(v) for v in t.split("x")) for t in args.tiles.split(",")]
+    subtiles = [tuple(int(v) for v in t.split("x")) for t in args.subtiles.split(",") if t] or [None]
+    extra = json.loads(args.extra) if args.extra else {}
+    candidates = []
+    for shape, budget, threads, stages, load, sub in itertools.product(
+            shapes, args.budgets.split(","), args.threads.split(","), args.stages.split(","),
+            args.loads.split(","), subtiles):
+        cuda = {"SMEM_BUDGET": int(budget) * 1024, "THREADS": int(threads), "STAGES": int(stages), "LOAD": load}
+        if sub:
+            cuda["SUBTILE"] = sub
+        cuda.update(extra)
+        candidates.append((args.kernel, assignment, shape, domain, cuda))
+    with ProcessPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+        built = list(pool.map(compile_one, candidates))
+
+    points = domain[0] * domain[1] * domain[2]
+    results = []
+    tensors = {}
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    for cand, (paths, err) in zip(candidates, built):
+        _, _, shape, _, cuda = cand
+        if paths is None:
+            print("skip", shape, cuda, err.splitlines()[-1] if err else "")
+            continue
+        v = Variant(paths[0], paths[1])
+        dims = (v.X, v.Y, v.Z, v.HX, v.HY, v.HZ)
+        for name in v.inputs + v.outputs:
+            if name not in tensors:
+                t = torch.rand(v.shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+                make_periodic(t, dims)
+                tensors[name] = t
+        v.bind([tensors[n] for n in v.inputs], [tensors[n] for n in v.outputs])
+        total, halo = v.run(args.runs, flush=False)
+        v.close()
+        program = make(*cand)
+        analyse(program)
+        bpp = algorithmic_bytes_per_point(program)
+        ms = statistics.median(total)
+        hms = statistics.median(halo)
+        row = {"tile": list(shape), "cuda": cuda, "total_ms": round(ms, 4), "halo_ms": round(hms, 4),
+               "mpoints_s": round(points / ms / 1e3, 1), "GBps_total": round(bpp * points / ms / 1e6, 1),
+               "GBps_kernels": round(bpp * points / (ms - hms) / 1e6, 1), "bytes_per_point": bpp}
+        results.append(row)
+        print(json.dumps(row), flush=True)
+    results.sort(key=lambda r: r["total_ms"])
+    if results:
+        print("BEST", json.dumps(results[0]))
+    if args.out:
+        os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
+        with open(args.out, "w") as handle:
+            json.dump({"kernel": args.kernel, "assignment": assignment, "domain": list(domain),
+                       "results": results}, handle, indent=1)
+    if args.save and results:
+        from absinthe_b200.analysis import ceil_div
+        path = os.path.join(ROOT, "absinthe_b200", "tuned.json")
+        tuned = json.load(open(path)) if os.path.exists(path) else {}
+        best = results[0]
+        counts = [max(1, ceil_div(d, s)) for d, s in zip(domain, best["tile"])]
+        tuned[args.kernel] = {"assignment": assignment, "tiles": [counts] * (max(assignment) + 1),
+                              "cuda": best["cuda"], "measured": {k: best[k] for k in ("total_ms", "GBps_total")}}
+        with open(path, "w") as handle:
+            json.dump(tuned, handle, indent=1)
+
+
+if __name__ == "__main__":
+    main()
