@@ -34,7 +34,10 @@ DEFAULTS = {
     "LOAD": "tma",               # "tma" | "ldg"
     "SUBTILE": None,             # (BX, BY, BZ) override
     "FMAD": False,               # False -> -fmad=false: bit-exact with the strict oracle
-    "FUSE_HALO": False,
+    "FUSE_HALO": False,          # periodic copies written by the producing kernel
+    "INLINE": "none",            # intermediates re-evaluated in registers: "none" | "all" | [names]
+    "DIRECT": "none",            # centre-only inputs read straight from global: "none" | "auto" | [names]
+    "BLOCK": (1, 1),             # (RJ, RK): points per thread along j and k
 }
 MAX_BOX = 256                    # TMA box limit per dimension
 ALIGN_DOUBLES = 16               # 128-byte alignment of every staged box
@@ -74,13 +77,25 @@ def _splits(extent):
 
 
 class GroupPlan:
-    """Everything needed to render and launch the kernel of one fused group."""
+    """Everything needed to render and launch the kernel of one fused group.
+
+    Stencils of the group fall into two classes.  *Materialised* stencils are evaluated over
+    their LOOPS-extended box by all threads of the CTA and stored -- group outputs to global
+    memory, intermediates that a later materialised stencil reads to shared memory.  *Inlined*
+    intermediates (option ``INLINE``) are never stored: wherever a consumer reads them they are
+    re-evaluated in registers from their own operands, memoised per thread.  Each thread owns a
+    ``1 x RJ x RK`` block of points (option ``BLOCK``), so neighbouring evaluations share their
+    loads and inlined values.  Materialised stencils with the same box that do not feed each
+    other through shared memory are evaluated together in one *phase*; phases are separated by
+    ``__syncthreads()`` where one reads what another wrote.
+    """
 
     def __init__(self, program, group, opts):
         self.program, self.group, self.opts = program, group, opts
         self.id = group["ID"] + 1          # kernel numbering follows the outer (schedule) id
         self.stencils = group["STENCILS"]
         self.names = [s["NAME"] for s in self.stencils]
+        self.by_name = {s["NAME"]: s for s in self.stencils}
         dims = (program["X"], program["Y"], program["Z"])
         self.S = dims
         self.H = (program["HX"], program["HY"], program["HZ"])
@@ -92,22 +107,58 @@ class GroupPlan:
         self.reach = A.group_reach(group)
         self.inputs = list(group["INPUTS"])
         self.outputs = list(group["OUTPUTS"])
-        # a stencil result lives in shared memory when a later stencil of the group reads it
-        self.read_later = set()
-        for n, s in enumerate(self.stencils):
-            for field in s["OFFSETS"]:
-                if field in self.names[:n]:
-                    self.read_later.add(field)
         self.row = dims[0] + 2 * self.H[0]
         self.plane = self.row * (dims[1] + 2 * self.H[1])
+        self.block = (1,) + tuple(opts["BLOCK"])
+        self._classify()
         self.load = opts["LOAD"]
-        if self.load == "tma" and (self.row % 2 or not self.inputs):
+        if self.load == "tma" and (self.row % 2 or not self.staged):
             self.load = "ldg"              # TMA needs 16-byte global strides
         self.stages = opts["STAGES"] if self.load == "tma" else 1
         self.threads = opts["THREADS"]
+        self.fuse_halo = bool(opts["FUSE_HALO"]) and all(s >= 2 * h for s, h in zip(dims, self.H))
         self.B = self._choose_subtile()
         self.nsub = tuple(A.ceil_div(t, b) for t, b in zip(self.T, self.B))
         self._layout()
+
+    # -- classification ---------------------------------------------------------------------
+    def _select(self, option, candidates):
+        if option in (None, "none", False):
+            return set()
+        if option in ("all", True):
+            return set(candidates)
+        return set(option) & set(candidates)
+
+    def _classify(self):
+        temps = [n for n in self.names if n not in self.outputs]
+        self.inlined = self._select(self.opts["INLINE"], temps)
+        self.materialised = [n for n in self.names if n not in self.inlined]
+        # fields a materialised stencil reads once its inlined operands are expanded
+        self.closure = {}
+        for name in self.names:
+            reads = {}
+            for field, box in self.by_name[name]["OFFSETS"].items():
+                if field in self.inlined:
+                    for inner, inner_box in self.closure[field].items():
+                        grown = A.box_add(inner_box, box)
+                        reads[inner] = A.box_widen(reads[inner], grown) if inner in reads else grown
+                else:
+                    reads[field] = A.box_widen(reads[field], box) if field in reads else box
+            self.closure[name] = reads
+        self.in_smem = [n for n in self.materialised
+                        if any(n in self.closure[m] for m in self.materialised if m != n)]
+        # a value that only feeds later stencils of its own phase at the same point stays in registers
+        self.phase_list = self._phases()
+        keep = []
+        for n in self.in_smem:
+            mine = next(ph for ph in self.phase_list if n in ph["NAMES"])
+            if any(n in self.closure[m] for m in self.materialised if m != n and m not in mine["NAMES"]):
+                keep.append(n)
+        self.in_smem = keep
+        centre_only = [n for n in self.inputs if self.reach[n] == A.ZERO_BOX]
+        direct = self.opts["DIRECT"]
+        self.direct = self._select("all" if direct == "auto" else direct, centre_only)
+        self.staged = [n for n in self.inputs if n not in self.direct]
 
     # -- shared-memory planning -----------------------------------------------------------
     def _box_dims(self, B, box, even_x=False):
@@ -119,16 +170,23 @@ class GroupPlan:
             d[0] = d[0] + 1 + (d[0] + 1) % 2
         return d
 
+    def _slack(self, B):
+        """Doubles a thread block may read past a box when its RJ x RK block overhangs the range."""
+        worst = 0
+        for name in self.staged + self.in_smem:
+            d = self._box_dims(B, self.reach[name], even_x=name in self.staged)
+            worst = max(worst, (self.block[1] - 1) * d[0] + (self.block[2] - 1) * d[0] * d[1])
+        return _round_up(worst, ALIGN_DOUBLES)
+
     def _footprint(self, B):
         total = 0
-        for name in self.inputs:
+        for name in self.staged:
             d = self._box_dims(B, self.reach[name], even_x=True)
             total += self.stages * _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
-        for name in self.names:
-            if name in self.read_later:
-                d = self._box_dims(B, self.reach[name])
-                total += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
-        return total * 8 + 64
+        for name in self.in_smem:
+            d = self._box_dims(B, self.reach[name])
+            total += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+        return (total + self._slack(B)) * 8 + 128
 
     def _cost(self, B):
         """Work per useful point of a sub-tile ``B``: staged cells (short rows cost extra: every
@@ -136,12 +194,12 @@ class GroupPlan:
         count, and a fixed price per work item (barriers, pipeline bubble)."""
         row_slack, item_overhead = 12, 3000
         moved = item_overhead
-        for name in self.inputs:
+        for name in self.staged:
             d = self._box_dims(B, self.reach[name], even_x=True)
             moved += (d[0] + row_slack) * d[1] * d[2]
-        for s in self.stencils:
-            d = self._box_dims(B, self.reach[s["NAME"]])
-            moved += d[0] * d[1] * d[2] * 0.25 * len(s["OFFSETS"])
+        for name in self.materialised:
+            d = self._box_dims(B, self.reach[name])
+            moved += d[0] * d[1] * d[2] * 0.25 * len(self.closure[name])
         return moved / float(B[0] * B[1] * B[2])
 
     def _choose_subtile(self):
@@ -156,7 +214,7 @@ class GroupPlan:
         budget = min(self.opts["SMEM_BUDGET"], SMEM_LIMIT)
         best = None
         for bx in _splits(self.T[0]):
-            if bx + widest[0] + 1 > MAX_BOX:
+            if bx + widest[0] + 2 > MAX_BOX:
                 continue
             for by in _splits(self.T[1]):
                 if by + widest[1] > MAX_BOX:
@@ -181,11 +239,13 @@ class GroupPlan:
         cursor = 0
         self.input_plan = []
         for n, name in enumerate(self.inputs):
+            if name in self.direct:
+                continue
             box = self.reach[name]
             d = self._box_dims(B, box, even_x=True)
             lo = [box[a][0] for a in range(3)]
             self.input_plan.append({
-                "NAME": name, "INDEX": n, "LO": lo, "DIM": d, "OFFSET": cursor,
+                "NAME": name, "INDEX": n, "MAP": len(self.input_plan), "LO": lo, "DIM": d, "OFFSET": cursor,
                 "ROW": d[0], "PLANE": d[0] * d[1], "CELLS": d[0] * d[1] * d[2],
                 # pointer bias so that relative (i, j, k) index the box directly
                 "BIAS": cursor - (lo[0] + lo[1] * d[0] + lo[2] * d[0] * d[1]),
@@ -195,9 +255,7 @@ class GroupPlan:
         self.stage_bytes = sum(p["CELLS"] for p in self.input_plan) * 8
         cursor = self.stages * self.stage_doubles
         self.temp_plan = {}
-        for name in self.names:
-            if name not in self.read_later:
-                continue
+        for name in self.in_smem:
             box = self.reach[name]
             d = self._box_dims(B, box)
             lo = [box[a][0] for a in range(3)]
@@ -206,6 +264,7 @@ class GroupPlan:
                 "BIAS": cursor - (lo[0] + lo[1] * d[0] + lo[2] * d[0] * d[1]),
             }
             cursor += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+        cursor += self._slack(B)
         self.barrier_offset = cursor * 8
         self.smem_bytes = cursor * 8 + 8 * max(self.stages, 1) + 48
         assert self.smem_bytes <= SMEM_LIMIT, "shared-memory plan exceeds the sm_100a limit"
@@ -216,13 +275,11 @@ class GroupPlan:
             for p in self.input_plan:
                 self.args.append(("tmap", off, p["NAME"], p["DIM"]))
                 off += 128
-        self.in_ptr_offset = off
         for name in self.inputs:
             self.args.append(("ptr", off, name, None))
             off += 8
         if not self.inputs:
             off += 8                        # the kernel declares at least one input slot
-        self.out_ptr_offset = off
         for name in self.outputs:
             self.args.append(("ptr", off, name, None))
             off += 8
@@ -230,49 +287,125 @@ class GroupPlan:
         off += 8
         self.params_bytes = _round_up(off, 64)
 
-    # -- stencil text -----------------------------------------------------------------------
-    def _rewrite(self, code):
-        """Replace every access by an indexed load from its staged box / intermediate."""
-        inputs = {p["NAME"]: p for p in self.input_plan}
+    # -- phases -----------------------------------------------------------------------------
+    def _phases(self):
+        """Group the materialised stencils into barrier-separated phases."""
+        phases = []
+        for name in self.materialised:
+            box = self.reach[name]
+            reads_smem = [f for f in self.closure[name] if f in self.in_smem]
+            direct_zero = {f for f, b in self.by_name[name]["OFFSETS"].items() if b == A.ZERO_BOX}
+            current = phases[-1] if phases else None
+            joinable = current is not None and current["BOX"] == box and all(
+                f not in current["NAMES"] or (f in direct_zero and self._only_direct(name, f))
+                for f in reads_smem)
+            if joinable:
+                current["NAMES"].append(name)
+            else:
+                phases.append({"BOX": box, "NAMES": [name]})
+        return phases
 
-        def access(match):
-            name = match.group(1)
-            off = [A._offset(match.group(n)) for n in (2, 3, 4)]
-            plan = inputs.get(name) or self.temp_plan.get(name)
-            assert plan is not None, "stencil reads unknown field " + name
-            terms = []
-            for sym, o, stride in zip("ijk", off, (1, plan["ROW"], plan["PLANE"])):
-                idx = sym if o == 0 else "(%s%+d)" % (sym, o)
-                terms.append(idx if stride == 1 else "%s*%d" % (idx, stride))
-            prefix = "in_" if name in inputs else "tmp_"
-            return "%s%s[%s]" % (prefix, name, " + ".join(terms))
+    def _only_direct(self, name, field):
+        """True when ``name`` reaches ``field`` only by its own zero-offset access (no inlined path)."""
+        for other in self.by_name[name]["OFFSETS"]:
+            if other in self.inlined and field in self.closure[other]:
+                return False
+        return True
 
-        return A._ACCESS.sub(access, code)
+    @staticmethod
+    def _tag(off):
+        return "_".join(("m%d" % -o) if o < 0 else str(o) for o in off)
+
+    def _phase_body(self, phase):
+        """Straight-line code for one thread: its RJ x RK block of every stencil of the phase."""
+        staged = {p["NAME"]: p for p in self.input_plan}
+        lines, memo = [], {}
+        same_phase = set(phase["NAMES"])
+
+        def const_index(off, row, plane):
+            return off[0] + off[1] * row + off[2] * plane
+
+        def value(field, off, point):
+            """C expression of ``field`` at block-relative offset ``off``."""
+            key = (field, off)
+            if key in memo:
+                return memo[key]
+            tag = "%s_%s" % (field, self._tag(off))
+            if field in staged:
+                p = staged[field]
+                var = "l_" + tag
+                lines.append("const double %s = in_%s[b_%s + (%d)];" % (
+                    var, field, field, const_index(off, p["ROW"], p["PLANE"])))
+            elif field in self.direct:
+                var = "l_" + tag
+                assert off[0] == 0, "direct inputs are centre-only"
+                lines.append("const double %s = ok_%d_%d ? __ldg(gin_%s + bg + (%dL)) : 0.0;" % (
+                    var, off[1], off[2], field, off[1] * self.row + off[2] * self.plane))
+            elif field in self.temp_plan and field not in same_phase:
+                p = self.temp_plan[field]
+                var = "l_" + tag
+                lines.append("const double %s = tmp_%s[b_%s + (%d)];" % (
+                    var, field, field, const_index(off, p["ROW"], p["PLANE"])))
+            elif field in same_phase:
+                raise AssertionError("phase split missed a dependence on " + field)
+            else:
+                assert field in self.inlined, "stencil reads unknown field " + field
+                var = evaluate(field, off, point)
+            memo[key] = var
+            return var
+
+        def evaluate(name, off, point):
+            """Emit ``name`` evaluated at ``off``; returns the variable holding its result."""
+            code = self.by_name[name]["LAMBDA"]
+            accesses = A.stencil_accesses(code)
+            for field, d in accesses:                       # operands first (emits their code)
+                value(field, tuple(o + e for o, e in zip(off, d)), point)
+
+            def sub(match):
+                d = tuple(A._offset(match.group(n)) for n in (2, 3, 4))
+                return memo[(match.group(1), tuple(o + e for o, e in zip(off, d)))]
+            var = "v_%s_%s" % (name, self._tag(off))
+            lines.append("double %s; { %s %s = res; }" % (var, A._ACCESS.sub(sub, code), var))
+            return var
+
+        stores = []
+        for rk in range(self.block[2]):
+            for rj in range(self.block[1]):
+                point = (0, rj, rk)
+                for name in phase["NAMES"]:
+                    var = evaluate(name, point, point)
+                    memo[(name, point)] = var
+                    stores.append((name, rj, rk, var))
+        return lines, stores
 
     def passes(self):
         out = []
-        pending = set()      # intermediates written since the last barrier
-        for s in self.stencils:
-            name = s["NAME"]
-            box = self.reach[name]
+        pending = set()
+        for phase in self.phase_list:
+            box = phase["BOX"]
             lo = [box[a][0] for a in range(3)]
             hi = [box[a][1] for a in range(3)]
             dim = self._box_dims(self.B, box)
-            reads_tmp = [f for f in s["OFFSETS"] if f in self.temp_plan]
-            sync_before = any(f in pending for f in reads_tmp)
+            blocks = [dim[0], A.ceil_div(dim[1], self.block[1]), A.ceil_div(dim[2], self.block[2])]
+            reads = set()
+            for name in phase["NAMES"]:
+                reads.update(f for f in self.closure[name] if f in self.temp_plan and f not in phase["NAMES"])
+            sync_before = bool(reads & pending)
             if sync_before:
                 pending.clear()
-            to_smem = name in self.temp_plan
-            if to_smem:
-                pending.add(name)
+            pending.update(n for n in phase["NAMES"] if n in self.temp_plan)
+            lines, stores = self._phase_body(phase)
             out.append({
-                "NAME": name, "LO": lo, "HI": hi, "DIM": dim, "CELLS": dim[0] * dim[1] * dim[2],
-                "CODE": self._rewrite(s["LAMBDA"]), "SYNC_BEFORE": sync_before,
-                "TO_SMEM": to_smem, "TEMP": self.temp_plan.get(name),
-                "TO_GLOBAL": name in self.outputs,
-                "OUT_INDEX": self.outputs.index(name) if name in self.outputs else -1,
-                "READS_INPUTS": [f for f in s["OFFSETS"] if f in self.inputs],
-                "READS_TEMPS": reads_tmp,
+                "NAMES": phase["NAMES"], "LO": lo, "HI": hi, "DIM": dim, "BLOCKS": blocks,
+                "CELLS": blocks[0] * blocks[1] * blocks[2], "SYNC_BEFORE": sync_before,
+                "BODY": lines,
+                "STORES": [{"NAME": n, "RJ": rj, "RK": rk, "VAR": var,
+                            "TEMP": self.temp_plan.get(n), "TO_GLOBAL": n in self.outputs} for n, rj, rk, var in stores],
+                "OUTPUTS": [{"NAME": n, "INDEX": self.outputs.index(n)} for n in phase["NAMES"] if n in self.outputs],
+                "READS_STAGED": sorted({f for n in phase["NAMES"] for f in self.closure[n] if f in self.staged}),
+                "READS_DIRECT": sorted({f for n in phase["NAMES"] for f in self.closure[n] if f in self.direct}),
+                "READS_TEMPS": sorted(reads),
+                "POINTS": [(rj, rk) for rk in range(self.block[2]) for rj in range(self.block[1])],
             })
         return out
 
@@ -283,11 +416,14 @@ class GroupPlan:
             "T": self.T, "O": self.O, "N": self.N, "B": self.B, "NSUB": self.nsub,
             "NSUB_TOTAL": self.nsub[0] * self.nsub[1] * self.nsub[2],
             "TILES": self.tiles, "INPUTS": self.input_plan, "NIN": len(self.inputs),
+            "NMAPS": len(self.input_plan),
+            "DIRECT": [{"NAME": n, "INDEX": self.inputs.index(n)} for n in self.inputs if n in self.direct],
             "OUTPUTS": self.outputs, "NOUT": len(self.outputs),
             "TEMPS": list(self.temp_plan.values()), "PASSES": self.passes(),
             "STAGE_DOUBLES": self.stage_doubles, "STAGE_BYTES": self.stage_bytes,
             "BARRIER_OFFSET": self.barrier_offset, "SMEM_BYTES": self.smem_bytes,
-            "PARAMS_BYTES": self.params_bytes, "NAMES": self.names,
+            "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
+            "BLOCK": self.block, "FUSE_HALO": self.fuse_halo,
         }
 
 
@@ -340,7 +476,7 @@ class Plan:
             lines.append("group %d kernel absinthe_group%d threads %d smem %d tiles %d params %d "
                          "training_step %d fused_halo %d" % (
                              g.id, g.id, g.threads, g.smem_bytes, g.tiles, g.params_bytes,
-                             training.get("STRIDE", 20), 0))
+                             training.get("STRIDE", 20), int(g.fuse_halo)))
             for kind, off, name, dim in g.args:
                 if kind == "tmap":
                     lines.append("arg tmap %d %s %d %d %d" % (off, name, dim[0], dim[1], dim[2]))

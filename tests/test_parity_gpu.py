@@ -23,5 +23,31 @@ def test_staged_loads_match_oracle(launcher_lib, name, program):
     assert_bit_exact(program)
 
 
+OPTIONS = [
+    ("inline-all", {"INLINE": "all"}),
+    ("inline-block2", {"INLINE": "all", "BLOCK": (2, 1)}),
+    ("inline-block4x2-direct-halo", {"INLINE": "all", "BLOCK": (4, 2), "DIRECT": "auto", "FUSE_HALO": True}),
+    ("block3-halo-ldg", {"BLOCK": (3, 1), "FUSE_HALO": True, "LOAD": "ldg", "DIRECT": "auto"}),
+    ("halo-512", {"FUSE_HALO": True, "THREADS": 512, "SMEM_BUDGET": 200 * 1024}),
+]
+PARTIAL_INLINE = {"diffusion": ["ufli", "uflj", "vfli", "vflj", "wfli", "wflj", "ppfli", "ppflj"],
+                  "advection": ["uatu", "vatu"], "fastwaves": ["ppgk", "ppgc", "udc"]}
+
+
+@pytest.mark.parametrize("label,cuda", OPTIONS, ids=[o[0] for o in OPTIONS])
+@pytest.mark.parametrize("name,program", CASES, ids=[c[0] for c in CASES])
+def test_emitter_options_match_oracle(launcher_lib, name, program, label, cuda):
+    program = P.clone(program)
+    program["CUDA"] = dict(cuda)
+    assert_bit_exact(program)
+
+
+@pytest.mark.parametrize("name,program", CASES, ids=[c[0] for c in CASES])
+def test_partial_inlining_matches_oracle(launcher_lib, name, program):
+    program = P.clone(program)
+    program["CUDA"] = {"INLINE": PARTIAL_INLINE[program["NAME"]], "BLOCK": (2, 2), "FUSE_HALO": True}
+    assert_bit_exact(program)
+
+
 def test_cuda_graph_replay(launcher_lib):
     assert_bit_exact(CASES[0][1], graph=True)

@@ -53,6 +53,7 @@ def main():
     ap.add_argument("--loads", default="tma")
     ap.add_argument("--subtiles", default="", help="optional comma list of BXxBYxBZ overrides")
     ap.add_argument("--extra", default="", help="JSON dict merged into every candidate's CUDA options")
+    ap.add_argument("--sweep", default="", help="JSON dict option -> list of values (full product)")
     ap.add_argument("--runs", type=int, default=4)
     ap.add_argument("--out", default="")
     ap.add_argument("--save", action="store_true", help="write the winner into absinthe_b200/tuned.json")
@@ -70,15 +71,20 @@ def main():
     shapes = [tuple(int(v) for v in t.split("x")) for t in args.tiles.split(",")]
     subtiles = [tuple(int(v) for v in t.split("x")) for t in args.subtiles.split(",") if t] or [None]
     extra = json.loads(args.extra) if args.extra else {}
+    sweep = json.loads(args.sweep) if args.sweep else {}
+    sweep_keys = sorted(sweep)
     candidates = []
     for shape, budget, threads, stages, load, sub in itertools.product(
             shapes, args.budgets.split(","), args.threads.split(","), args.stages.split(","),
             args.loads.split(","), subtiles):
-        cuda = {"SMEM_BUDGET": int(budget) * 1024, "THREADS": int(threads), "STAGES": int(stages), "LOAD": load}
-        if sub:
-            cuda["SUBTILE"] = sub
-        cuda.update(extra)
-        candidates.append((args.kernel, assignment, shape, domain, cuda))
+        for combo in itertools.product(*[sweep[k] for k in sweep_keys]):
+            cuda = {"SMEM_BUDGET": int(budget) * 1024, "THREADS": int(threads), "STAGES": int(stages),
+                    "LOAD": load}
+            if sub:
+                cuda["SUBTILE"] = sub
+            cuda.update(extra)
+            cuda.update(dict(zip(sweep_keys, combo)))
+            candidates.append((args.kernel, assignment, shape, domain, cuda))
     with ProcessPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
         built = list(pool.map(compile_one, candidates))
 
