@@ -38,7 +38,9 @@ DEFAULTS = {
     "INLINE": "none",            # intermediates re-evaluated in registers: "none" | "all" | [names]
     "DIRECT": "none",            # centre-only inputs read straight from global: "none" | "auto" | [names]
     "BLOCK": (1, 1),             # (RJ, RK): points per thread along j and k
+    "SHUFFLE": False,            # inlined intermediates at i-offsets come from neighbour lanes
 }
+FRONT_SLACK = 16                 # doubles before the first box (halo lanes of a warp read below it)
 MAX_BOX = 256                    # TMA box limit per dimension
 ALIGN_DOUBLES = 16               # 128-byte alignment of every staged box
 
@@ -176,6 +178,8 @@ class GroupPlan:
         for name in self.staged + self.in_smem:
             d = self._box_dims(B, self.reach[name], even_x=name in self.staged)
             worst = max(worst, (self.block[1] - 1) * d[0] + (self.block[2] - 1) * d[0] * d[1])
+        if self.opts["SHUFFLE"]:
+            worst += 48                     # lanes of the last warp segment past the end of a row
         return _round_up(worst, ALIGN_DOUBLES)
 
     def _footprint(self, B):
@@ -186,7 +190,7 @@ class GroupPlan:
         for name in self.in_smem:
             d = self._box_dims(B, self.reach[name])
             total += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
-        return (total + self._slack(B)) * 8 + 128
+        return (total + self._slack(B) + FRONT_SLACK) * 8 + 128
 
     def _cost(self, B):
         """Work per useful point of a sub-tile ``B``: staged cells (short rows cost extra: every
@@ -237,6 +241,7 @@ class GroupPlan:
     def _layout(self):
         B = self.B
         cursor = 0
+        self.front = FRONT_SLACK if self.opts["SHUFFLE"] else 0
         self.input_plan = []
         for n, name in enumerate(self.inputs):
             if name in self.direct:
@@ -264,7 +269,7 @@ class GroupPlan:
                 "BIAS": cursor - (lo[0] + lo[1] * d[0] + lo[2] * d[0] * d[1]),
             }
             cursor += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
-        cursor += self._slack(B)
+        cursor += self._slack(B) + self.front
         self.barrier_offset = cursor * 8
         self.smem_bytes = cursor * 8 + 8 * max(self.stages, 1) + 48
         assert self.smem_bytes <= SMEM_LIMIT, "shared-memory plan exceeds the sm_100a limit"
@@ -289,21 +294,28 @@ class GroupPlan:
 
     # -- phases -----------------------------------------------------------------------------
     def _phases(self):
-        """Group the materialised stencils into barrier-separated phases."""
-        phases = []
+        """Group the materialised stencils into barrier-separated phases.
+
+        A stencil may share a phase with a producer it reads only at its own point (the value
+        is still in the thread's registers) when both cover the same box; every other
+        shared-memory dependence puts it one level later.  Stencils of equal level and box form
+        one phase, so e.g. the four laplacians of a fused diffusion group are one sweep.
+        """
+        level = {}
         for name in self.materialised:
-            box = self.reach[name]
-            reads_smem = [f for f in self.closure[name] if f in self.in_smem]
+            box, lv = self.reach[name], 0
             direct_zero = {f for f, b in self.by_name[name]["OFFSETS"].items() if b == A.ZERO_BOX}
-            current = phases[-1] if phases else None
-            joinable = current is not None and current["BOX"] == box and all(
-                f not in current["NAMES"] or (f in direct_zero and self._only_direct(name, f))
-                for f in reads_smem)
-            if joinable:
-                current["NAMES"].append(name)
-            else:
-                phases.append({"BOX": box, "NAMES": [name]})
-        return phases
+            for f in self.closure[name]:
+                if f not in level:
+                    continue
+                free = (f in direct_zero and self._only_direct(name, f) and self.reach[f] == box)
+                lv = max(lv, level[f] + (0 if free else 1))
+            level[name] = lv
+        phases = {}
+        for name in self.materialised:
+            phases.setdefault((level[name], self.reach[name]), []).append(name)
+        order = sorted(phases, key=lambda key: (key[0], self.names.index(phases[key][0])))
+        return [{"BOX": key[1], "NAMES": phases[key]} for key in order]
 
     def _only_direct(self, name, field):
         """True when ``name`` reaches ``field`` only by its own zero-offset access (no inlined path)."""
@@ -317,15 +329,21 @@ class GroupPlan:
         return "_".join(("m%d" % -o) if o < 0 else str(o) for o in off)
 
     def _phase_body(self, phase):
-        """Straight-line code for one thread: its RJ x RK block of every stencil of the phase."""
+        """Straight-line code for one thread: its RJ x RK block of every stencil of the phase.
+
+        Returns (lines, stores, lanes).  With SHUFFLE an inlined intermediate wanted at an
+        i-offset is taken from the neighbour lane that evaluated it at its own column;
+        ``lanes = (first, last)`` are the lanes of a warp whose results are then complete.
+        """
         staged = {p["NAME"]: p for p in self.input_plan}
-        lines, memo = [], {}
+        shuffle = bool(self.opts["SHUFFLE"])
+        lines, memo, lanes = [], {}, {}
         same_phase = set(phase["NAMES"])
 
         def const_index(off, row, plane):
             return off[0] + off[1] * row + off[2] * plane
 
-        def value(field, off, point):
+        def value(field, off):
             """C expression of ``field`` at block-relative offset ``off``."""
             key = (field, off)
             if key in memo:
@@ -336,47 +354,63 @@ class GroupPlan:
                 var = "l_" + tag
                 lines.append("const double %s = in_%s[b_%s + (%d)];" % (
                     var, field, field, const_index(off, p["ROW"], p["PLANE"])))
+                lanes[var] = (0, 31)
             elif field in self.direct:
                 var = "l_" + tag
                 assert off[0] == 0, "direct inputs are centre-only"
                 lines.append("const double %s = ok_%d_%d ? __ldg(gin_%s + bg + (%dL)) : 0.0;" % (
                     var, off[1], off[2], field, off[1] * self.row + off[2] * self.plane))
+                lanes[var] = (0, 31)
             elif field in self.temp_plan and field not in same_phase:
                 p = self.temp_plan[field]
                 var = "l_" + tag
                 lines.append("const double %s = tmp_%s[b_%s + (%d)];" % (
                     var, field, field, const_index(off, p["ROW"], p["PLANE"])))
+                lanes[var] = (0, 31)
             elif field in same_phase:
                 raise AssertionError("phase split missed a dependence on " + field)
             else:
                 assert field in self.inlined, "stencil reads unknown field " + field
-                var = evaluate(field, off, point)
+                if shuffle and off[0] != 0:
+                    own = value(field, (0, off[1], off[2]))
+                    var = "s_" + tag
+                    fn = "__shfl_down_sync" if off[0] > 0 else "__shfl_up_sync"
+                    lines.append("const double %s = %s(0xffffffffu, %s, %d);" % (var, fn, own, abs(off[0])))
+                    lo, hi = lanes[own]
+                    lanes[var] = (max(0, lo - off[0]), min(31, hi - off[0]))
+                else:
+                    var = evaluate(field, off)
             memo[key] = var
             return var
 
-        def evaluate(name, off, point):
+        def evaluate(name, off):
             """Emit ``name`` evaluated at ``off``; returns the variable holding its result."""
             code = self.by_name[name]["LAMBDA"]
-            accesses = A.stencil_accesses(code)
-            for field, d in accesses:                       # operands first (emits their code)
-                value(field, tuple(o + e for o, e in zip(off, d)), point)
+            lo, hi = 0, 31
+            for field, d in A.stencil_accesses(code):       # operands first (emits their code)
+                operand = value(field, tuple(o + e for o, e in zip(off, d)))
+                lo, hi = max(lo, lanes[operand][0]), min(hi, lanes[operand][1])
 
             def sub(match):
                 d = tuple(A._offset(match.group(n)) for n in (2, 3, 4))
                 return memo[(match.group(1), tuple(o + e for o, e in zip(off, d)))]
             var = "v_%s_%s" % (name, self._tag(off))
             lines.append("double %s; { %s %s = res; }" % (var, A._ACCESS.sub(sub, code), var))
+            lanes[var] = (lo, hi)
             return var
 
         stores = []
+        first, last = 0, 31
         for rk in range(self.block[2]):
             for rj in range(self.block[1]):
                 point = (0, rj, rk)
                 for name in phase["NAMES"]:
-                    var = evaluate(name, point, point)
+                    var = evaluate(name, point)
                     memo[(name, point)] = var
                     stores.append((name, rj, rk, var))
-        return lines, stores
+                    first, last = max(first, lanes[var][0]), min(last, lanes[var][1])
+        assert first <= last, "shuffle chain longer than a warp"
+        return lines, stores, (first, last)
 
     def passes(self):
         out = []
@@ -394,8 +428,12 @@ class GroupPlan:
             if sync_before:
                 pending.clear()
             pending.update(n for n in phase["NAMES"] if n in self.temp_plan)
-            lines, stores = self._phase_body(phase)
+            lines, stores, lanes = self._phase_body(phase)
+            useful = lanes[1] - lanes[0] + 1
+            nseg = A.ceil_div(dim[0], useful)
             out.append({
+                "SHUFFLE": bool(self.opts["SHUFFLE"]), "LANES": lanes, "USEFUL": useful, "NSEG": nseg,
+                "TASKS": nseg * blocks[1] * blocks[2],
                 "NAMES": phase["NAMES"], "LO": lo, "HI": hi, "DIM": dim, "BLOCKS": blocks,
                 "CELLS": blocks[0] * blocks[1] * blocks[2], "SYNC_BEFORE": sync_before,
                 "BODY": lines,
@@ -423,7 +461,8 @@ class GroupPlan:
             "STAGE_DOUBLES": self.stage_doubles, "STAGE_BYTES": self.stage_bytes,
             "BARRIER_OFFSET": self.barrier_offset, "SMEM_BYTES": self.smem_bytes,
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
-            "BLOCK": self.block, "FUSE_HALO": self.fuse_halo,
+            "BLOCK": self.block, "FUSE_HALO": self.fuse_halo, "FRONT": self.front,
+            "WARPS": self.threads // 32,
         }
 
 

@@ -29,6 +29,8 @@ OPTIONS = [
     ("inline-block4x2-direct-halo", {"INLINE": "all", "BLOCK": (4, 2), "DIRECT": "auto", "FUSE_HALO": True}),
     ("block3-halo-ldg", {"BLOCK": (3, 1), "FUSE_HALO": True, "LOAD": "ldg", "DIRECT": "auto"}),
     ("halo-512", {"FUSE_HALO": True, "THREADS": 512, "SMEM_BUDGET": 200 * 1024}),
+    ("shuffle", {"INLINE": "all", "SHUFFLE": True, "FUSE_HALO": True}),
+    ("shuffle-block4x2", {"INLINE": "all", "SHUFFLE": True, "BLOCK": (4, 2), "DIRECT": "auto", "THREADS": 128}),
 ]
 PARTIAL_INLINE = {"diffusion": ["ufli", "uflj", "vfli", "vflj", "wfli", "wflj", "ppfli", "ppflj"],
                   "advection": ["uatu", "vatu"], "fastwaves": ["ppgk", "ppgc", "udc"]}
@@ -46,6 +48,8 @@ def test_emitter_options_match_oracle(launcher_lib, name, program, label, cuda):
 def test_partial_inlining_matches_oracle(launcher_lib, name, program):
     program = P.clone(program)
     program["CUDA"] = {"INLINE": PARTIAL_INLINE[program["NAME"]], "BLOCK": (2, 2), "FUSE_HALO": True}
+    assert_bit_exact(program)
+    program["CUDA"]["SHUFFLE"] = True
     assert_bit_exact(program)
 
 

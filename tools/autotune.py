@@ -44,8 +44,9 @@ def compile_one(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--kernel", required=True)
-    ap.add_argument("--assignment", required=True, help="group index per stencil, e.g. 0000111122223333")
-    ap.add_argument("--tiles", required=True, help="comma list of tile shapes TXxTYxTZ")
+    ap.add_argument("--assignment", default="", help="group index per stencil, e.g. 0000111122223333")
+    ap.add_argument("--tiles", default="", help="comma list of tile shapes TXxTYxTZ")
+    ap.add_argument("--from-tuned", action="store_true", help="time the variant recorded in tuned.json")
     ap.add_argument("--domain", default="1024x1024x80")
     ap.add_argument("--budgets", default="110", help="shared-memory budgets per CTA in KiB")
     ap.add_argument("--threads", default="256")
@@ -67,6 +68,14 @@ def main():
     build_launcher()
 
     domain = tuple(int(v) for v in args.domain.split("x"))
+    if args.from_tuned:
+        from absinthe_b200.analysis import ceil_div
+        cfg = json.load(open(os.path.join(ROOT, "absinthe_b200", "tuned.json")))[args.kernel]
+        args.assignment = "".join(str(a) for a in cfg["assignment"])
+        args.tiles = "x".join(str(ceil_div(d, n)) for d, n in zip(domain, cfg["tiles"][0]))
+        args.extra = json.dumps(cfg.get("cuda", {}))
+        args.budgets = str(cfg.get("cuda", {}).get("SMEM_BUDGET", 110 * 1024) // 1024)
+        args.threads = str(cfg.get("cuda", {}).get("THREADS", 256))
     assignment = [int(c) for c in args.assignment]
     shapes = [tuple(int(v) for v in t.split("x")) for t in args.tiles.split(",")]
     subtiles = [tuple(int(v) for v in t.split("x")) for t in args.subtiles.split(",") if t] or [None]
