@@ -271,7 +271,8 @@ class GroupPlan:
             cursor += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
         cursor += self._slack(B) + self.front
         self.barrier_offset = cursor * 8
-        self.smem_bytes = cursor * 8 + 8 * max(self.stages, 1) + 48
+        self.smem_bytes = cursor * 8 + 16 * max(self.stages, 1) + 48
+        self.launch_threads = self.threads + (32 if self.load == "tma" else 0)
         assert self.smem_bytes <= SMEM_LIMIT, "shared-memory plan exceeds the sm_100a limit"
         # parameter block: tensor maps (128 B each, 64-byte aligned), pointers, tile control
         off = 0
@@ -462,7 +463,7 @@ class GroupPlan:
             "BARRIER_OFFSET": self.barrier_offset, "SMEM_BYTES": self.smem_bytes,
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
             "BLOCK": self.block, "FUSE_HALO": self.fuse_halo, "FRONT": self.front,
-            "WARPS": self.threads // 32,
+            "WARPS": self.threads // 32, "LAUNCH_THREADS": self.launch_threads,
         }
 
 
@@ -514,7 +515,7 @@ class Plan:
         for g in self.groups:
             lines.append("group %d kernel absinthe_group%d threads %d smem %d tiles %d params %d "
                          "training_step %d fused_halo %d" % (
-                             g.id, g.id, g.threads, g.smem_bytes, g.tiles, g.params_bytes,
+                             g.id, g.id, g.launch_threads, g.smem_bytes, g.tiles, g.params_bytes,
                              training.get("STRIDE", 20), int(g.fuse_halo)))
             for kind, off, name, dim in g.args:
                 if kind == "tmap":
