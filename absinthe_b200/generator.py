@@ -78,7 +78,7 @@ def render(template, program):
     plan = Plan(program)
     context = plan.context()
     context["TRAINING"] = template == "template_training.cu"
-    source = _environment().get_template("template_tiling.cu").render(context)
+    source = _environment().get_template(template).render(context)
     return source, plan.descriptor_text(), plan.nvcc_flags()
 
 
@@ -124,9 +124,11 @@ def generate_script(name, experiments, cores, runs):
         handle.write("#!/bin/bash -l\n")
         handle.write("# CORES in the variant description = %s SMs of the target GPU\n\n" % cores)
         handle.write("export CUDA_DEVICE_MAX_CONNECTIONS=1\n\n")
+        # one interpreter start per repetition: the runner takes any number of variants and prints
+        # the same per-variant protocol as one process each would
         for _ in range(runs):
-            for key in experiments:
-                handle.write("%s -m absinthe_b200.runner ./%s\n" % (os.path.basename(sys.executable), key))
+            handle.write("%s -m absinthe_b200.runner \\\n" % os.path.basename(sys.executable))
+            handle.write(" \\\n".join("    ./" + key for key in experiments) + "\n")
 
 
 def parse_results(results, skip=16):

@@ -41,6 +41,7 @@ def run_variant(stem, runs, flush=True, training=False, device=0, out=sys.stdout
     outputs = [variant.empty_field() for _ in variant.outputs]
     variant.bind(inputs, outputs)
     total, halo = variant.run(runs, flush=flush, training=training)
+    variant.close()
     for t, h in zip(total, halo):
         print("-> apply stencils...", file=out)
         print("   - total time (min/median/max) [ms]: %g" % t, file=out)
@@ -50,21 +51,23 @@ def run_variant(stem, runs, flush=True, training=False, device=0, out=sys.stdout
 
 def main(argv=None):
     parser = argparse.ArgumentParser(description=__doc__.split("\n")[0])
-    parser.add_argument("stem", help="path of the variant without extension")
+    parser.add_argument("stem", nargs="+", help="path(s) of the variant(s) without extension")
     parser.add_argument("--runs", type=int, default=None, help="timed runs (default: RUNS of the program)")
     parser.add_argument("--no-flush", action="store_true")
     parser.add_argument("--device", type=int, default=0)
     args = parser.parse_args(argv)
-    meta = {}
-    with open(args.stem + ".desc") as handle:
-        for line in handle:
-            if line.startswith("# "):
-                key, _, value = line[2:].strip().partition(" ")
-                meta[key] = value
-    runs = args.runs or int(meta.get("runs", 64))
-    flush = not args.no_flush and meta.get("flush", "1") == "1"
-    training = meta.get("training", "0") == "1"
-    run_variant(args.stem, runs, flush=flush, training=training, device=args.device)
+    for stem in args.stem:
+        meta = {}
+        with open(stem + ".desc") as handle:
+            for line in handle:
+                if line.startswith("# "):
+                    key, _, value = line[2:].strip().partition(" ")
+                    meta[key] = value
+        runs = args.runs or int(meta.get("runs", 64))
+        flush = not args.no_flush and meta.get("flush", "1") == "1"
+        training = meta.get("training", "0") == "1"
+        run_variant(stem, runs, flush=flush, training=training, device=args.device)
+        sys.stdout.flush()
 
 
 if __name__ == "__main__":

@@ -1,0 +1,9 @@
+#!/usr/bin/env python
+"""fastwaves experiment driver on the B200 backend -- same flags as the reference's fastwaves.py
+(see absinthe_b200/driver.py)."""
+import sys
+
+from absinthe_b200.driver import main
+
+if __name__ == "__main__":
+    main("fastwaves", sys.argv[1:])

@@ -1,0 +1,9 @@
+#!/usr/bin/env python
+"""fitcache experiment driver on the B200 backend -- same flags as the reference's fitcache.py
+(see absinthe_b200/driver.py)."""
+import sys
+
+from absinthe_b200.driver import main
+
+if __name__ == "__main__":
+    main("fitcache", sys.argv[1:])
