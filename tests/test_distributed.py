@@ -1,0 +1,108 @@
+"""Multi-rank halo exchange: the protocol on CPU (gloo, world_size 2) and the full path on >= 2 GPUs."""
+
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from absinthe_b200.distributed import SlabExchange, face_rows, neighbours
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_neighbours_wrap():
+    assert neighbours(0, 4) == (3, 1) and neighbours(3, 4) == (2, 0) and neighbours(0, 1) == (0, 0)
+    assert face_rows(64, 3) == ((3, 3), (64, 3), (0, 3), (67, 3))
+
+
+class HostExchange(SlabExchange):
+    """Test double: same protocol, fields are CPU tensors and the face kernels are slicing."""
+
+    def __init__(self, fields, dims, world, rank):
+        self.fields, self.dims, self.world, self.rank, self.pg = fields, dims, world, rank, None
+        self.prev, self.next = neighbours(rank, world)
+        self.buffers = {}
+
+    def field_names(self, group):
+        return sorted(self.fields)
+
+    def allocate(self, count):
+        X, Y, Z, HX, HY, HZ = self.dims
+        return [torch.empty((count, Z + 2 * HZ, HY, X + 2 * HX), dtype=torch.float64) for _ in range(4)]
+
+    def local_faces(self, name):
+        X, Y, Z, HX, HY, HZ = self.dims
+        f = self.fields[name]
+        f[:, :, :HX] = f[:, :, X:X + HX]
+        f[:, :, X + HX:] = f[:, :, HX:2 * HX]
+        f[:HZ] = f[Z:Z + HZ]
+        f[Z + HZ:] = f[HZ:2 * HZ]
+
+    def pack(self, name, buffer, j0, width):
+        buffer.copy_(self.fields[name][:, j0:j0 + width, :])
+
+    def unpack(self, name, buffer, j0, width):
+        self.fields[name][:, j0:j0 + width, :] = buffer
+
+
+def _worker(rank, world, port, dims, failures):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    X, Y, Z, HX, HY, HZ = dims
+    rng = np.random.default_rng(5)
+    names = ["a", "b"]
+    glob = {n: rng.standard_normal((Z, world * Y, X)) for n in names}
+    fields = {}
+    for n in names:
+        local = np.zeros((Z + 2 * HZ, Y + 2 * HY, X + 2 * HX))
+        local[HZ:HZ + Z, HY:HY + Y, HX:HX + X] = glob[n][:, rank * Y:(rank + 1) * Y, :]
+        fields[n] = torch.from_numpy(local)
+    HostExchange(fields, dims, world, rank).update(1)
+    for n in names:
+        padded = np.pad(glob[n], ((HZ, HZ), (HY, HY), (HX, HX)), mode="wrap")
+        want = padded[:, rank * Y:rank * Y + Y + 2 * HY, :]
+        if not np.array_equal(fields[n].numpy(), want):
+            failures.put((rank, n))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_slab_exchange_protocol_gloo(world):
+    ctx = mp.get_context("spawn")
+    failures = ctx.Queue()
+    port = 29500 + os.getpid() % 1000 + world
+    procs = [ctx.Process(target=_worker, args=(r, world, port, (12, 7, 5, 3, 3, 3), failures)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert failures.empty()
+
+
+def test_single_rank_exchange_is_make_periodic():
+    dims = (10, 6, 4, 3, 3, 3)
+    X, Y, Z, HX, HY, HZ = dims
+    rng = np.random.default_rng(1)
+    interior = rng.standard_normal((Z, Y, X))
+    local = np.zeros((Z + 6, Y + 6, X + 6))
+    local[3:3 + Z, 3:3 + Y, 3:3 + X] = interior
+    fields = {"f": torch.from_numpy(local)}
+    HostExchange(fields, dims, 1, 0).update(1)
+    assert np.array_equal(fields["f"].numpy(), np.pad(interior, 3, mode="wrap"))
+
+
+@pytest.mark.gpu
+def test_two_gpus_match_one(launcher_lib):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29611", os.path.join(ROOT, "tests", "multi_gpu_check.py")]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
+    assert "multi-gpu parity ok" in proc.stdout
