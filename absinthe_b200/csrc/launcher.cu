@@ -215,6 +215,29 @@ __global__ void pack_kernel(const double* __restrict__ field, double* __restrict
     }
 }
 
+// both j-faces of every field of a list in one launch: buffers are [field][plane][HY][row];
+// pack reads the first / last HY interior rows, unpack writes the low / high halo rows
+__global__ void faces_kernel(FieldList fields, double* low, double* high, Geometry g, int unpack) {
+    const long row = g.row(), plane = g.plane();
+    const long per_field = g.planes() * g.HY * row;
+    const long total = 2 * fields.count * per_field;
+    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < total;
+         n += (long)gridDim.x * blockDim.x) {
+        const int side = (int)(n / (fields.count * per_field));
+        const long m = n % (fields.count * per_field);
+        const int f = (int)(m / per_field);
+        const long r = m % per_field;
+        const long k = r / (g.HY * row), q = r % (g.HY * row);
+        // pack: low side = rows [HY, 2HY), high side = rows [Y, Y+HY)
+        // unpack: low buffer -> rows [0, HY), high buffer -> rows [Y+HY, Y+2HY)
+        const long j0 = unpack ? (side ? g.Y + g.HY : 0) : (side ? g.Y : g.HY);
+        const long at = k * plane + (j0 + q / row) * row + q % row;
+        double* buffer = side ? high : low;
+        if (unpack) fields.ptr[f][at] = buffer[m];
+        else buffer[m] = fields.ptr[f][at];
+    }
+}
+
 int launch_grid(long items, int threads) {
     long blocks = (items + threads - 1) / threads;
     return (int)std::max(1L, std::min(blocks, 148L * 16));
@@ -289,6 +312,8 @@ struct absinthe_variant {
     bool bound = false;
     cudaGraphExec_t graph = nullptr;
     cudaStream_t graph_stream = nullptr;
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
     std::vector<cudaEvent_t> events;
 };
 
@@ -531,6 +556,10 @@ void absinthe_variant_free(absinthe_variant* v) {
     cudaSetDevice(v->device);
     if (v->graph) cudaGraphExecDestroy(v->graph);
     if (v->graph_stream) cudaStreamDestroy(v->graph_stream);
+    if (v->h2d_stream) cudaStreamDestroy(v->h2d_stream);
+    if (v->d2h_stream) cudaStreamDestroy(v->d2h_stream);
+    for (cudaEvent_t e : {v->ev_in, v->ev_done, v->ev_out})
+        if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : v->events) cudaEventDestroy(e);
     for (Field& f : v->fields)
         if (f.owned && f.ptr) cudaFree(f.ptr);
@@ -657,6 +686,40 @@ int absinthe_variant_halo_group(absinthe_variant* v, int group, void* stream) {
     return fail(-3, "variant '%s' has no group %d", v->name.c_str(), group);
 }
 
+static int group_faces(absinthe_variant* v, int group, double* low, double* high, int local_faces, int unpack,
+                       void* stream) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    for (Group& g : v->groups)
+        if (g.id == group) {
+            if (g.halo_fields.empty()) return 0;
+            FieldList list{};
+            list.count = (int)g.halo_fields.size();
+            for (int n = 0; n < list.count; ++n) list.ptr[n] = v->fields[g.halo_fields[n]].ptr;
+            const Geometry& q = v->geo;
+            if (local_faces && !unpack && !g.fused_halo) {
+                if (!(q.X >= q.HX && q.Z >= q.HZ)) return fail(-3, "extent smaller than halo");
+                long cells = 2L * q.HZ * q.plane() + (long)q.Z * q.Y * 2 * q.HX;
+                periodic_kernel<<<launch_grid(cells, 256), 256, 0, (cudaStream_t)stream>>>(list, q, 5);
+            }
+            long total = 2L * list.count * q.planes() * q.HY * q.row();
+            faces_kernel<<<launch_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(list, low, high, q, unpack);
+            RT(cudaGetLastError());
+            return 0;
+        }
+    return fail(-3, "variant '%s' has no group %d", v->name.c_str(), group);
+}
+
+int absinthe_variant_pack_group(absinthe_variant* v, int group, double* d_low, double* d_high, int local_faces,
+                                void* stream) {
+    return group_faces(v, group, d_low, d_high, local_faces, 0, stream);
+}
+
+int absinthe_variant_unpack_group(absinthe_variant* v, int group, const double* d_low, const double* d_high,
+                                  void* stream) {
+    return group_faces(v, group, const_cast<double*>(d_low), const_cast<double*>(d_high), 0, 1, stream);
+}
+
 int absinthe_variant_group_outputs(const absinthe_variant* v, int group) {
     if (!v) return 0;
     for (const Group& g : v->groups)
@@ -736,6 +799,38 @@ int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inpu
     for (size_t n = 0; n < v->outputs.size(); ++n)
         RT(cudaMemcpyAsync(h_outputs[n], v->fields[v->outputs[n]].ptr, bytes, cudaMemcpyDeviceToHost, s));
     RT(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int absinthe_variant_apply_host_async(absinthe_variant* v, const double* const* h_inputs,
+                                      double* const* h_outputs, void* stream) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (!v->h2d_stream) {
+        RT(cudaStreamCreateWithFlags(&v->h2d_stream, cudaStreamNonBlocking));
+        RT(cudaStreamCreateWithFlags(&v->d2h_stream, cudaStreamNonBlocking));
+        RT(cudaEventCreateWithFlags(&v->ev_in, cudaEventDisableTiming));
+        RT(cudaEventCreateWithFlags(&v->ev_done, cudaEventDisableTiming));
+        RT(cudaEventCreateWithFlags(&v->ev_out, cudaEventDisableTiming));
+    }
+    const size_t bytes = absinthe_variant_field_bytes(v);
+    for (size_t n = 0; n < v->inputs.size(); ++n)
+        RT(cudaMemcpyAsync(v->fields[v->inputs[n]].ptr, h_inputs[n], bytes, cudaMemcpyHostToDevice, v->h2d_stream));
+    RT(cudaEventRecord(v->ev_in, v->h2d_stream));
+    RT(cudaStreamWaitEvent(s, v->ev_in, 0));
+    if ((rc = absinthe_variant_apply(v, s))) return rc;
+    RT(cudaEventRecord(v->ev_done, s));
+    RT(cudaStreamWaitEvent(v->d2h_stream, v->ev_done, 0));
+    for (size_t n = 0; n < v->outputs.size(); ++n)
+        RT(cudaMemcpyAsync(h_outputs[n], v->fields[v->outputs[n]].ptr, bytes, cudaMemcpyDeviceToHost, v->d2h_stream));
+    RT(cudaEventRecord(v->ev_out, v->d2h_stream));
+    return 0;
+}
+
+int absinthe_variant_wait_host(absinthe_variant* v) {
+    if (!v) return fail(-3, "null variant");
+    if (v->ev_out) RT(cudaEventSynchronize(v->ev_out));
     return 0;
 }
 

@@ -66,6 +66,26 @@ class SlabExchange:
         check(lib, lib.absinthe_halo_unpack(self.v.field_ptr(name), buffer.data_ptr(), *self.dims, j0, width,
                                             _stream_handle(None)), "absinthe_halo_unpack")
 
+    def pack_all(self, group, names, send_low, send_high):
+        """Local i/k faces + both j-faces of all outputs of the group (one launch each on the GPU)."""
+        if hasattr(self.v, "pack_group"):
+            self.v.pack_group(group, send_low, send_high, local_faces=True)
+            return
+        low_int, high_int, _, _ = face_rows(self.dims[1], self.dims[4])
+        for n, name in enumerate(names):
+            self.local_faces(name)
+            self.pack(name, send_low[n], *low_int)
+            self.pack(name, send_high[n], *high_int)
+
+    def unpack_all(self, group, names, recv_low, recv_high):
+        if hasattr(self.v, "unpack_group"):
+            self.v.unpack_group(group, recv_low, recv_high)
+            return
+        _, _, low_halo, high_halo = face_rows(self.dims[1], self.dims[4])
+        for n, name in enumerate(names):
+            self.unpack(name, recv_low[n], *low_halo)
+            self.unpack(name, recv_high[n], *high_halo)
+
     # -- protocol ---------------------------------------------------------------------------
     def update(self, group):
         """PUT + WAIT of every output of ``group`` (the slot after its COMP in the schedule)."""
@@ -76,11 +96,7 @@ class SlabExchange:
         if group not in self.buffers:
             self.buffers[group] = self.allocate(len(names))
         send_low, send_high, recv_low, recv_high = self.buffers[group]
-        low_int, high_int, low_halo, high_halo = face_rows(self.dims[1], self.dims[4])
-        for n, name in enumerate(names):
-            self.local_faces(name)
-            self.pack(name, send_low[n], *low_int)
-            self.pack(name, send_high[n], *high_int)
+        self.pack_all(group, names, send_low, send_high)
         if self.world == 1:
             recv_high.copy_(send_low)
             recv_low.copy_(send_high)
@@ -91,6 +107,4 @@ class SlabExchange:
                    dist.P2POp(dist.irecv, recv_low, self.prev, self.pg)]
             for work in dist.batch_isend_irecv(ops):
                 work.wait()
-        for n, name in enumerate(names):
-            self.unpack(name, recv_low[n], *low_halo)
-            self.unpack(name, recv_high[n], *high_halo)
+        self.unpack_all(group, names, recv_low, recv_high)

@@ -26,6 +26,8 @@ SYMBOLS = [
     "absinthe_variant_group_output", "absinthe_variant_field_ptr", "absinthe_variant_run",
     "absinthe_variant_apply_host", "absinthe_make_periodic", "absinthe_fill_rand", "absinthe_flush_l2",
     "absinthe_halo_pack", "absinthe_halo_unpack", "absinthe_make_periodic_ik",
+    "absinthe_variant_pack_group", "absinthe_variant_unpack_group",
+    "absinthe_variant_apply_host_async", "absinthe_variant_wait_host",
 ]
 
 
@@ -71,6 +73,8 @@ def load_library(path=None):
                                          c.POINTER(c.c_float), c.POINTER(c.c_float)]
     lib.absinthe_variant_apply_host.argtypes = [c.c_void_p, c.POINTER(c.c_void_p), c.POINTER(c.c_void_p),
                                                 c.c_void_p]
+    lib.absinthe_variant_apply_host_async.argtypes = lib.absinthe_variant_apply_host.argtypes
+    lib.absinthe_variant_wait_host.argtypes = [c.c_void_p]
     lib.absinthe_make_periodic.argtypes = [c.c_void_p] + [c.c_int] * 6 + [c.c_void_p]
     lib.absinthe_make_periodic_ik.argtypes = [c.c_void_p] + [c.c_int] * 6 + [c.c_void_p]
     lib.absinthe_fill_rand.argtypes = [c.c_void_p, c.c_size_t, c.c_uint, c.c_int]
@@ -78,6 +82,8 @@ def load_library(path=None):
     lib.absinthe_flush_l2.argtypes = [c.c_void_p]
     lib.absinthe_halo_pack.argtypes = [c.c_void_p, c.c_void_p] + [c.c_int] * 8 + [c.c_void_p]
     lib.absinthe_halo_unpack.argtypes = [c.c_void_p, c.c_void_p] + [c.c_int] * 8 + [c.c_void_p]
+    lib.absinthe_variant_pack_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_void_p]
+    lib.absinthe_variant_unpack_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -185,6 +191,14 @@ class Variant:
         check(self.lib, self.lib.absinthe_variant_halo_group(self.handle, group, _stream_handle(stream)),
               "halo_group")
 
+    def pack_group(self, group, low, high, local_faces=True, stream=None):
+        check(self.lib, self.lib.absinthe_variant_pack_group(self.handle, group, low.data_ptr(), high.data_ptr(),
+                                                             int(local_faces), _stream_handle(stream)), "pack_group")
+
+    def unpack_group(self, group, low, high, stream=None):
+        check(self.lib, self.lib.absinthe_variant_unpack_group(self.handle, group, low.data_ptr(), high.data_ptr(),
+                                                               _stream_handle(stream)), "unpack_group")
+
     def group_outputs(self, group):
         n = self.lib.absinthe_variant_group_outputs(self.handle, group)
         return [self.lib.absinthe_variant_group_output(self.handle, group, k).decode() for k in range(n)]
@@ -200,11 +214,17 @@ class Variant:
                                                       int(training), total, halo), "absinthe_variant_run")
         return list(total), list(halo)
 
-    def apply_host(self, host_inputs, host_outputs, stream=None):
-        """End to end with HOST (pinned) tensors: H2D, apply, D2H, synchronised."""
-        check(self.lib, self.lib.absinthe_variant_apply_host(
-            self.handle, _pointer_array([t.data_ptr() for t in host_inputs]),
-            _pointer_array([t.data_ptr() for t in host_outputs]), _stream_handle(stream)), "apply_host")
+    def apply_host(self, host_inputs, host_outputs, stream=None, wait=True):
+        """End to end with HOST (pinned) tensors: H2D, apply, D2H.  ``wait=False`` returns while the
+        copies are in flight on the variant's private copy streams (finish with ``wait_host``)."""
+        fn = self.lib.absinthe_variant_apply_host if wait else self.lib.absinthe_variant_apply_host_async
+        check(self.lib, fn(self.handle, _pointer_array([t.data_ptr() for t in host_inputs]),
+                           _pointer_array([t.data_ptr() for t in host_outputs]), _stream_handle(stream)),
+              "apply_host")
+        self._host = (host_inputs, host_outputs)
+
+    def wait_host(self):
+        check(self.lib, self.lib.absinthe_variant_wait_host(self.handle), "wait_host")
 
 
 # ---- field helpers -----------------------------------------------------------------------

@@ -105,7 +105,7 @@ class ClockSampler(threading.Thread):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
         except Exception:
@@ -279,13 +279,13 @@ def run_gpu_arm(args):
                     c.record()
                     record.append((item["name"], g, a, b, c))
 
+    sampler = ClockSampler(local)
+    sampler.start()
     for _ in range(max(args.warmup, 3)):
         step()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
     records = []
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
@@ -351,8 +351,10 @@ def run_gpu_arm(args):
             dist.barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            for v, hin, hout in host:
-                v.apply_host(hin, hout)
+            for v, hin, hout in host:            # copies of the two sequences overlap (H2D || D2H)
+                v.apply_host(hin, hout, wait=False)
+            for v, _, _ in host:
+                v.wait_host()
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
         if world > 1:
@@ -363,7 +365,7 @@ def run_gpu_arm(args):
         d2h = sum(len(hout) for _, _, hout in host) * host[0][0].field_bytes
         e2e = {"value": round(2 * points * world / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpoints/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 2),
-               "steps": e2e_steps, "api": "Variant.apply_host (absinthe_variant_apply_host)"}
+               "steps": e2e_steps, "api": "Variant.apply_host(wait=False) + wait_host (absinthe_variant_apply_host_async)"}
 
     if rank == 0:
         line = {
@@ -388,7 +390,7 @@ def run_gpu_arm(args):
 def main():
     parser = argparse.ArgumentParser()
     parser.add_argument("--gpus", type=int, default=1)
-    parser.add_argument("--steps", type=int, default=20)
+    parser.add_argument("--steps", type=int, default=100)
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="absinthe_b200", choices=["absinthe_b200", "reference"])
     parser.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

@@ -105,6 +105,13 @@ int absinthe_variant_run(absinthe_variant* v, void* stream, int runs, int flush,
 int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inputs,
                                 double* const* h_outputs, void* stream);
 
+/* The same without the final synchronisation: H2D on a private copy stream, the sequence on `stream`,
+ * D2H on a second copy stream, so the copies of several variants overlap (full-duplex PCIe).
+ * absinthe_variant_wait_host blocks until the outputs of the last async call are in host memory. */
+int absinthe_variant_apply_host_async(absinthe_variant* v, const double* const* h_inputs,
+                                      double* const* h_outputs, void* stream);
+int absinthe_variant_wait_host(absinthe_variant* v);
+
 /* ---- field helpers ----------------------------------------------------------------------- */
 
 /* periodic boundary condition on a device field (i, then j, then k faces; corners consistent) */
@@ -123,6 +130,13 @@ int absinthe_halo_pack(const double* d_field, double* d_buffer, int X, int Y, in
                        int HY, int HZ, int j0, int width, void* stream);
 int absinthe_halo_unpack(double* d_field, const double* d_buffer, int X, int Y, int Z, int HX,
                          int HY, int HZ, int j0, int width, void* stream);
+/* All outputs of `group` at once: pack their first / last HY interior rows into d_low / d_high
+ * ([field][plane][HY][X+2HX], one launch; local_faces != 0 first refreshes the i and k periodic faces
+ * unless the group kernel already wrote them), and unpack received rows into the low / high j-halo. */
+int absinthe_variant_pack_group(absinthe_variant* v, int group, double* d_low, double* d_high,
+                                int local_faces, void* stream);
+int absinthe_variant_unpack_group(absinthe_variant* v, int group, const double* d_low,
+                                  const double* d_high, void* stream);
 /* periodic update restricted to the i and k faces (the j faces come from the neighbour ranks) */
 int absinthe_make_periodic_ik(double* d_field, int X, int Y, int Z, int HX, int HY, int HZ,
                               void* stream);

@@ -24,7 +24,7 @@ class HostExchange(SlabExchange):
     """Test double: same protocol, fields are CPU tensors and the face kernels are slicing."""
 
     def __init__(self, fields, dims, world, rank):
-        self.fields, self.dims, self.world, self.rank, self.pg = fields, dims, world, rank, None
+        self.fields, self.dims, self.world, self.rank, self.pg, self.v = fields, dims, world, rank, None, None
         self.prev, self.next = neighbours(rank, world)
         self.buffers = {}
 
