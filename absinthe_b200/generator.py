@@ -123,7 +123,8 @@ def generate_script(name, experiments, cores, runs):
     with open(name, "w", newline="\n") as handle:
         handle.write("#!/bin/bash -l\n")
         handle.write("# CORES in the variant description = %s SMs of the target GPU\n\n" % cores)
-        handle.write("export CUDA_DEVICE_MAX_CONNECTIONS=1\n\n")
+        package_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+        handle.write("export PYTHONPATH=%s:$PYTHONPATH\n\n" % package_root)
         # one interpreter start per repetition: the runner takes any number of variants and prints
         # the same per-variant protocol as one process each would
         for _ in range(runs):

@@ -1,12 +1,12 @@
 #!/bin/bash
 # training sweep on the GPU: generate, build, run, parse, fit (ref README "Training" recipe)
 mkdir -p gpurun_out
-timeout 300 python -m pytest tests/test_parity_gpu.py -x -q -k training > gpurun_out/pytest_training.log 2>&1; echo "pytest exit $?" > gpurun_out/status.txt
+echo skip > gpurun_out/status.txt
 for FAM in fitcache fitddr; do
   rm -rf /tmp/$FAM; mkdir -p /tmp/$FAM
   ( time python $FAM.py -g -f /tmp/$FAM ) > gpurun_out/${FAM}_gen.log 2>&1
   ( cd /tmp/$FAM && time make -j16 ) > gpurun_out/${FAM}_make.log 2>&1; echo "$FAM make exit $?" >> gpurun_out/status.txt
-  ( cd /tmp/$FAM && time bash run.sh > output.txt ) 2> gpurun_out/${FAM}_run.log; echo "$FAM run exit $?" >> gpurun_out/status.txt
+  ( cd /tmp/$FAM && time bash run.sh > output.txt ) > gpurun_out/${FAM}_run.log 2>&1; echo "$FAM run exit $?" >> gpurun_out/status.txt
   python $FAM.py -p output.txt -f /tmp/$FAM > /dev/null
   cp /tmp/$FAM/results.csv gpurun_out/${FAM}_results.csv
 done
