@@ -59,21 +59,31 @@ def r_squared(design, target, coef):
     return 1.0 - float(np.sum((target - pred) ** 2) / np.sum((target - target.mean()) ** 2))
 
 
-def fit_cache(rows, cores, nonnegative=False):
-    """``{"BODY", "PEEL"}`` from a fitcache sweep (ref fitcache.R:27-50; PT8 is excluded, ``fac >= 10``)."""
+def _with_intercept(design, intercept):
+    return np.concatenate([design, np.ones((len(design), 1))], axis=1) if intercept else design
+
+
+def fit_cache(rows, cores, nonnegative=False, intercept=False):
+    """``{"BODY", "PEEL"}`` from a fitcache sweep (ref fitcache.R:27-50; PT8 is excluded, ``fac >= 10``).
+
+    ``intercept`` adds a constant column: on a GPU one wave of small tiles is dominated by the launch
+    and pipeline-fill latency, which the reference's through-the-origin model cannot express."""
     fac = np.array([float(r[0][2:]) for r in rows])
     keep = fac >= 10
     rows = [r for r, k in zip(rows, keep) if k]
     fac = fac[keep]
     t = _tile_terms(rows, cores)
-    design = np.stack([fac * STEPS * t["XYZ"], fac * STEPS * t["YZ"]], axis=1)
+    design = _with_intercept(np.stack([fac * STEPS * t["XYZ"], fac * STEPS * t["YZ"]], axis=1), intercept)
     target = np.array([r[4] for r in rows])
     coef = lad(design, target, nonnegative)
-    return {"BODY": coef[0] / cores, "PEEL": coef[1] / cores, "R2": r_squared(design, target, coef),
-            "SAMPLES": len(rows)}
+    out = {"BODY": coef[0] / cores, "PEEL": coef[1] / cores, "R2": r_squared(design, target, coef),
+           "SAMPLES": len(rows)}
+    if intercept:
+        out["LAUNCH"] = coef[2]
+    return out
 
 
-def fit_ddr(rows, cores, nonnegative=False):
+def fit_ddr(rows, cores, nonnegative=False, intercept=False):
     """``{"RW BODY", "ST BODY", "RW PEEL", "ST PEEL"}`` from a fitddr sweep (ref fitddr.R:27-56)."""
     inp = np.array([float(r[0][2]) for r in rows])
     keep = inp >= 1
@@ -85,12 +95,14 @@ def fit_ddr(rows, cores, nonnegative=False):
     st_body = STEPS * (inp + 1) * t["XYZ"] + STEPS * inp * bd * (t["XY"] + t["XZ"] + t["YZ"])
     rw_peel = STEPS * t["YZ"]
     st_peel = STEPS * (inp + 1) * t["YZ"] + STEPS * inp * bd * (t["Y"] + t["Z"])
-    design = np.stack([rw_body, st_body, rw_peel, st_peel], axis=1)
+    design = _with_intercept(np.stack([rw_body, st_body, rw_peel, st_peel], axis=1), intercept)
     target = np.array([r[4] for r in rows])
     coef = lad(design, target, nonnegative)
     names = ("RW BODY", "ST BODY", "RW PEEL", "ST PEEL")
     out = {n: c / cores for n, c in zip(names, coef)}
     out.update(R2=r_squared(design, target, coef), SAMPLES=len(rows))
+    if intercept:
+        out["LAUNCH"] = coef[4]
     return out
 
 
@@ -126,12 +138,13 @@ def main(argv=None):
     ap.add_argument("--ddr", help="fitddr results.csv")
     ap.add_argument("--cores", type=int, default=148)
     ap.add_argument("--nonnegative", action="store_true")
+    ap.add_argument("--intercept", action="store_true", help="fit a constant launch-latency term as well")
     args = ap.parse_args(argv)
     out = {}
     if args.cache:
-        out["CACHE"] = fit_cache(load_results(args.cache), args.cores, args.nonnegative)
+        out["CACHE"] = fit_cache(load_results(args.cache), args.cores, args.nonnegative, args.intercept)
     if args.ddr:
-        out["MEMORY"] = fit_ddr(load_results(args.ddr), args.cores, args.nonnegative)
+        out["MEMORY"] = fit_ddr(load_results(args.ddr), args.cores, args.nonnegative, args.intercept)
     print(json.dumps(out, indent=1))
 
 

@@ -13,11 +13,22 @@ import sys
 import numpy as np
 
 
-def prepare_inputs(variant, seed=0):
-    """Device tensors initialised exactly like the reference's main() (ref :209-221)."""
+def prepare_inputs(variant, seed=0, on_device=False):
+    """Device tensors initialised exactly like the reference's main() (ref :209-221).
+
+    ``on_device`` draws the values on the GPU instead (training sweeps: the domains are large, the
+    values irrelevant, and a host-side rand() fill of up to 27 fields dominated the run time)."""
     import torch
     from .launcher import make_periodic, reference_inputs
     dims = (variant.X, variant.Y, variant.Z, variant.HX, variant.HY, variant.HZ)
+    if on_device:
+        gen = torch.Generator(device="cuda:%d" % variant.device).manual_seed(seed)
+        tensors = []
+        for _ in variant.inputs:
+            t = torch.rand(variant.shape, dtype=torch.float64, device="cuda:%d" % variant.device, generator=gen)
+            make_periodic(t, dims)
+            tensors.append(t)
+        return tensors
     host = reference_inputs(len(variant.inputs), variant.shape, seed)
     tensors = []
     for array in host:
@@ -37,7 +48,7 @@ def run_variant(stem, runs, flush=True, training=False, device=0, out=sys.stdout
     print("   - domain %d, %d, %d" % (variant.X, variant.Y, variant.Z), file=out)
     print("   - runs %d" % runs, file=out)
     print("   - device " + torch.cuda.get_device_name(device), file=out)
-    inputs = prepare_inputs(variant)
+    inputs = prepare_inputs(variant, on_device=training)
     outputs = [variant.empty_field() for _ in variant.outputs]
     variant.bind(inputs, outputs)
     total, halo = variant.run(runs, flush=flush, training=training)
