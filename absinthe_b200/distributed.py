@@ -86,6 +86,32 @@ class SlabExchange:
             self.unpack(name, recv_low[n], *low_halo)
             self.unpack(name, recv_high[n], *high_halo)
 
+    # -- overlap ------------------------------------------------------------------------------
+    def update_async(self, group):
+        """PUT on a side stream: the exchange of ``group`` runs concurrently with whatever the caller
+        launches next on its own stream; ``wait(group)`` is the matching WAIT (ref schedule slots,
+        stencil_generator.py:23-37)."""
+        import torch
+        if not hasattr(self, "comm"):
+            self.comm = torch.cuda.Stream(device=self.v.device)
+            self.done = {}
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        with torch.cuda.stream(self.comm):
+            self.comm.wait_event(ready)
+            self.update(group)
+            done = torch.cuda.Event()
+            done.record(self.comm)
+        self.done[group] = done
+
+    def wait(self, group):
+        """Make the caller's stream wait for the outstanding exchange of ``group`` (if any)."""
+        import torch
+        done = getattr(self, "done", {}).pop(group, None)
+        if done is not None:
+            torch.cuda.current_stream().wait_event(done)
+
     # -- protocol ---------------------------------------------------------------------------
     def update(self, group):
         """PUT + WAIT of every output of ``group`` (the slot after its COMP in the schedule)."""

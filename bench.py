@@ -263,8 +263,12 @@ def run_gpu_arm(args):
 
     def step(record=None):
         for item in variants:
-            v = item["v"]
+            v, exchange = item["v"], item["exchange"]
             for g in range(1, v.n_groups + 1):
+                if exchange is not None:
+                    exchange.wait(g)              # last step's exchange still reads these outputs
+                    if g > 1:
+                        exchange.wait(g - 1)      # WAIT: this group reads the halos of the previous one
                 if record is not None:
                     a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                     a.record()
@@ -272,8 +276,8 @@ def run_gpu_arm(args):
                     b.record()
                 else:
                     v.apply_group(g, with_halo=False)
-                if item["exchange"] is not None:
-                    item["exchange"].update(g)
+                if exchange is not None:
+                    exchange.update_async(g)      # PUT, overlapped with the next kernels
                 else:
                     v.halo_group(g)
                 if record is not None:
@@ -293,6 +297,10 @@ def run_gpu_arm(args):
     start.record()
     for _ in range(args.steps):
         step(records)
+    for item in variants:                         # drain the exchanges still in flight
+        if item["exchange"] is not None:
+            for g in range(1, item["v"].n_groups + 1):
+                item["exchange"].wait(g)
     stop.record()
     torch.cuda.synchronize()
     elapsed_ms = start.elapsed_time(stop)

@@ -40,8 +40,15 @@ def run_case(kernel, groups, tiles, local_domain, cuda, rank, world):
     vl.bind(lin, lout)
     exchange = SlabExchange(vl, world, rank)
     for g in range(1, vl.n_groups + 1):
+        if g > 1:
+            exchange.wait(g - 1)
         vl.apply_group(g, with_halo=False)
-        exchange.update(g)
+        if g % 2:
+            exchange.update_async(g)          # both flavours of the PUT/WAIT pair are exercised
+        else:
+            exchange.update(g)
+    for g in range(1, vl.n_groups + 1):
+        exchange.wait(g)
     torch.cuda.synchronize()
     for name, mine, whole in zip(vl.outputs, lout, gout):
         want = whole[:, rank * Y:rank * Y + Y + 6, :]
