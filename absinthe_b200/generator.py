@@ -178,13 +178,17 @@ def build_variant(program, template="template_tiling.cu", cache_dir=None):
     os.makedirs(cache_dir, exist_ok=True)
     stem = os.path.join(cache_dir, tag)
     if not (os.path.exists(stem + ".cubin") and os.path.exists(stem + ".desc")):
-        with open(stem + ".cu", "w") as handle:
+        # several ranks may build the same variant at once: everything goes through per-process
+        # temporaries and is published with atomic renames
+        mine = "%s.%d" % (stem, os.getpid())
+        with open(mine + ".cu", "w") as handle:
             handle.write(source)
-        tmp = "%s.%d.tmp" % (stem, os.getpid())
-        proc = subprocess.run(nvcc_command(flags, stem + ".cu", tmp), capture_output=True, text=True)
+        proc = subprocess.run(nvcc_command(flags, mine + ".cu", mine + ".tmp"), capture_output=True, text=True)
         if proc.returncode != 0:
-            raise RuntimeError("nvcc failed for %s:\n%s" % (stem + ".cu", proc.stderr[-4000:]))
-        os.replace(tmp, stem + ".cubin")
-        with open(stem + ".desc", "w") as handle:
+            raise RuntimeError("nvcc failed for %s:\n%s" % (mine + ".cu", proc.stderr[-4000:]))
+        with open(mine + ".desc.tmp", "w") as handle:
             handle.write(descriptor)
+        os.replace(mine + ".cu", stem + ".cu")
+        os.replace(mine + ".tmp", stem + ".cubin")
+        os.replace(mine + ".desc.tmp", stem + ".desc")
     return stem + ".desc", stem + ".cubin"

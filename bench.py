@@ -231,8 +231,11 @@ def run_gpu_arm(args):
         os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout (one JSON line only)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
-    if local == 0:
+    if local == 0:                                 # one rank builds, the others wait for the cache
         build_launcher()
+        from absinthe_b200.generator import build_variant
+        for _, program in workload_programs():
+            build_variant(P.clone(program))
     if world > 1:
         dist.barrier()
 
