@@ -1,0 +1,57 @@
+"""The measurement protocol and the awkward corners of the variant space, on the GPU."""
+
+import io
+
+import numpy as np
+import pytest
+
+from absinthe_b200 import generator as G
+from absinthe_b200 import programs as P
+from common import assert_bit_exact, seq
+
+pytestmark = pytest.mark.gpu
+
+
+def test_runner_prints_the_reference_protocol(launcher_lib, tmp_path):
+    from absinthe_b200.runner import run_variant
+    import subprocess
+    program = P.make_program("advection", [seq("advection")], [(1, 4, 5)], variant="advection-0-1-4-5", RUNS=5)
+    stem = str(tmp_path / "advection-0-1-4-5")
+    G.generate_code("template_tiling.cu", stem + ".cu", program)
+    subprocess.check_call(G.nvcc_command(program["CUDA"]["NVCC_FLAGS"], stem + ".cu", stem + ".cubin"))
+    out = io.StringIO()
+    total, halo = run_variant(stem, 5, flush=True, out=out)
+    assert len(total) == 5 and np.all(total > 0) and np.all(halo > 0) and np.all(total > halo)   # TOTAL includes HALO
+    log = tmp_path / "output.txt"
+    log.write_text(out.getvalue())
+    rows = G.parse_results(str(log), 0)
+    assert len(rows) == 5 and rows[0][:4] == ["advection-0-1-4-5", "64", "64", "60"]
+    assert len(G.parse_results(str(log), 2)) == 3
+
+
+CORNERS = [
+    # more tiles than points along x and z: most tiles are empty after clipping
+    ("more-tiles-than-points", P.make_program("advection", [seq("advection")], [(24, 2, 9)], domain=(12, 10, 4))),
+    # extents smaller than the halo: the literal three-pass periodic update is needed
+    ("extent-below-halo", P.make_program("diffusion", [seq("diffusion")], [(1, 1, 1)], domain=(8, 2, 2))),
+    ("single-point-tiles", P.make_program("fastwaves", [seq("fastwaves")[:6], seq("fastwaves")[6:]],
+                                          [(8, 6, 4), (1, 1, 1)], domain=(8, 6, 4))),
+    ("one-long-row", P.make_program("advection", [seq("advection")], [(1, 1, 1)], domain=(600, 4, 3))),
+]
+
+
+@pytest.mark.parametrize("name,program", CORNERS, ids=[c[0] for c in CORNERS])
+@pytest.mark.parametrize("cuda", [{}, {"INLINE": "all", "BLOCK": (2, 2), "SHUFFLE": True, "FUSE_HALO": True}],
+                         ids=["generic", "tuned-options"])
+def test_corner_cases_match_oracle(launcher_lib, name, program, cuda):
+    program = P.clone(program)
+    program["CUDA"] = dict(cuda)
+    assert_bit_exact(program)
+
+
+def test_unbound_variant_is_an_error(launcher_lib):
+    from absinthe_b200.launcher import LauncherError, Variant
+    v = Variant.from_program(P.make_program("advection", domain=(16, 8, 4)))
+    with pytest.raises(LauncherError, match="no buffers bound"):
+        v.apply()
+    v.close()
