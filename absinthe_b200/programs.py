@@ -23,6 +23,11 @@ B200_SMEM_PER_CTA = 227 * 1024
 CPU_MEMORY = {"RW BODY": -2.23e-7, "ST BODY": 5.71e-7, "RW PEEL": -1.25e-6, "ST PEEL": 5.25e-6}
 CPU_CACHE = {"BODY": 9.44e-8, "PEEL": 9.95e-7}
 
+# GPU fit of the training sweeps (profiles/r01_fit_nonnegative_intercept.json, absinthe_b200/fit.py with
+# a launch-latency intercept of 10.2 us and non-negative coefficients; the RW terms fit to zero)
+B200_MEMORY = {"RW BODY": 0.0, "ST BODY": 4.91e-9, "RW PEEL": 0.0, "ST PEEL": 2.75e-8}
+B200_CACHE = {"BODY": 1.17e-10, "PEEL": 2.33e-10}
+
 KERNELS = {
     "diffusion": (S.diffusion_stencils, S.diffusion_sequence, S.DIFFUSION_OUTPUTS, S.DIFFUSION_CONSTANTS),
     "advection": (S.advection_stencils, S.advection_sequence, S.ADVECTION_OUTPUTS, S.ADVECTION_CONSTANTS),
@@ -38,8 +43,8 @@ def base_program(kernel, machine=None, memory=None, cache=None):
         "CONSTANTS": list(constants),
         "OUTPUTS": list(outputs),
         "MACHINE": dict(machine or {"CORES": B200_SMS, "CAPACITY": B200_SMEM_PER_CTA}),
-        "MEMORY": dict(memory or CPU_MEMORY),
-        "CACHE": dict(cache or CPU_CACHE),
+        "MEMORY": dict(memory or B200_MEMORY),
+        "CACHE": dict(cache or B200_CACHE),
         "OVERLAP": 1.0,
         "SLACK": {"SIZE": 0.02, "CORES": 0.05},
         "CONSTRAINTS": {},
