@@ -227,6 +227,10 @@ class GroupPlan:
                     if bz + widest[2] > MAX_BOX:
                         continue
                     B = (bx, by, bz)
+                    # a thread's RJ x RK block should not overhang the sub-tile
+                    if any(B[a] % self.block[a] and B[a] != self.T[a] and self.T[a] >= self.block[a]
+                           for a in (1, 2)):
+                        continue
                     if self._footprint(B) > budget:
                         continue
                     key = (round(self._cost(B), 3), -bx * by * bz)

@@ -45,6 +45,9 @@ def plan(args):
         except (SystemExit, Exception) as exc:
             print("skip", a, exc)
             continue
+        if "TILING" not in program or "OBJECTIVE" not in program:
+            print("skip (no incumbent within the time limit)", a)
+            continue
         tiles = [[g["GROUPS"][0][k] for k in ("NX", "NY", "NZ")] for g in program["TILING"]["GROUPS"]]
         variants.append({"assignment": a, "tiles": tiles, "estimate": float(program["OBJECTIVE"])})
         print(program["VARIANT"], tiles, program["OBJECTIVE"], flush=True)
