@@ -39,6 +39,7 @@ DEFAULTS = {
     "DIRECT": "none",            # centre-only inputs read straight from global: "none" | "auto" | [names]
     "BLOCK": (1, 1),             # (RJ, RK): points per thread along j and k
     "SHUFFLE": False,            # inlined intermediates at i-offsets come from neighbour lanes
+    "BRANCH": False,             # expensive ?: arms become real (warp-coherent) branches
 }
 FRONT_SLACK = 16                 # doubles before the first box (halo lanes of a warp read below it)
 MAX_BOX = 256                    # TMA box limit per dimension
@@ -76,6 +77,63 @@ def _splits(extent):
             seen.add(b)
             out.append(b)
     return out
+
+
+def branchify(code, threshold=8):
+    """Turn ``cond ? a : b`` with expensive arms into a real branch.
+
+    C++ evaluates only the selected arm of ``?:`` anyway, so the values (and their rounding) are
+    unchanged; what changes is that the compiler no longer if-converts the statement into evaluating
+    *both* arms and selecting (advection: two 6-tap polynomials per direction, ref advection.py:19-54).
+    With warp-coherent data -- wind direction does not flip between neighbouring columns -- the
+    branch halves the fp64 work.  Cheap arms (the flux limiter of diffusion) stay selects.
+    """
+    out, counter = [], 0
+    for statement in code.split(";"):
+        while "?" in statement:
+            q = statement.index("?")
+            depth, start = 0, None
+            for n in range(q - 1, -1, -1):               # start of the enclosing group
+                c = statement[n]
+                if c == ")":
+                    depth += 1
+                elif c == "(":
+                    if depth == 0:
+                        start = n + 1
+                        break
+                    depth -= 1
+                elif c == "=" and depth == 0 and statement[n - 1] not in "<>!=" and statement[n + 1] != "=":
+                    start = n + 1
+                    break
+            if start is None:
+                break
+            depth, colon, end = 0, None, len(statement)
+            for n in range(q + 1, len(statement)):
+                c = statement[n]
+                if c == "(":
+                    depth += 1
+                elif c == ")":
+                    if depth == 0:
+                        end = n
+                        break
+                    depth -= 1
+                elif c == ":" and depth == 0 and colon is None:
+                    colon = n
+                elif c == "?" and depth == 0:
+                    colon = -1                       # nested conditional at the same level: leave it
+                    break
+            if colon is None or colon < 0:
+                break
+            cond, a, b = statement[start:q], statement[q + 1:colon], statement[colon + 1:end]
+            if sum(a.count(op) + b.count(op) for op in "+-*/") < threshold:
+                break
+            name = "sel_%d" % counter
+            counter += 1
+            out.append("double %s; if (%s) { %s = %s; asm volatile(\"\"); } else { %s = %s; asm volatile(\"\"); }"
+                       % (name, cond.strip(), name, a.strip(), name, b.strip()))
+            statement = statement[:start] + " " + name + " " + statement[end:]
+        out.append(statement)
+    return ";".join(out)
 
 
 class GroupPlan:
@@ -400,7 +458,10 @@ class GroupPlan:
                 d = tuple(A._offset(match.group(n)) for n in (2, 3, 4))
                 return memo[(match.group(1), tuple(o + e for o, e in zip(off, d)))]
             var = "v_%s_%s" % (name, self._tag(off))
-            lines.append("double %s; { %s %s = res; }" % (var, A._ACCESS.sub(sub, code), var))
+            body = A._ACCESS.sub(sub, code)
+            if self.opts["BRANCH"]:
+                body = branchify(body)
+            lines.append("double %s; { %s %s = res; }" % (var, body, var))
             lanes[var] = (lo, hi)
             return var
 

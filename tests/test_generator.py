@@ -87,3 +87,16 @@ def test_makefile_and_script(tmp_path):
     assert "a.cubin: a.cu" in make and "arch=compute_100a,code=sm_100a" in make and "-fmad=false" in make
     script = (tmp_path / "run.sh").read_text()
     assert script.count("absinthe_b200.runner") == 2 and script.count("./a") == 2 and script.count("./b") == 2
+
+
+def test_branchify_only_touches_expensive_conditionals():
+    from absinthe_b200.emitter import branchify
+    from absinthe_b200 import stencils as S
+    cheap = S.diffusion_stencils()["ufli"]
+    assert branchify(cheap) == cheap                      # the flux limiter stays a select
+    adv = S.advection_stencils()
+    out = branchify(adv["utev"])
+    assert out.count("if (vatu(i,j,k) > 0.0)") == 1 and "?" not in out
+    assert out.rstrip().endswith("auto res = uteu(i,j,k) + ( sel_0 );")
+    top = branchify(adv["uteu"])
+    assert top.count("if (uatu(i,j,k) > 0.0)") == 1 and "auto res = sel_0 ;" in top

@@ -31,6 +31,7 @@ OPTIONS = [
     ("halo-512", {"FUSE_HALO": True, "THREADS": 512, "SMEM_BUDGET": 200 * 1024}),
     ("shuffle", {"INLINE": "all", "SHUFFLE": True, "FUSE_HALO": True}),
     ("shuffle-block4x2", {"INLINE": "all", "SHUFFLE": True, "BLOCK": (4, 2), "DIRECT": "auto", "THREADS": 128}),
+    ("branch", {"INLINE": "all", "BRANCH": True, "BLOCK": (2, 1), "FUSE_HALO": True}),
 ]
 PARTIAL_INLINE = {"diffusion": ["ufli", "uflj", "vfli", "vflj", "wfli", "wflj", "ppfli", "ppflj"],
                   "advection": ["uatu", "vatu"], "fastwaves": ["ppgk", "ppgc", "udc"]}
