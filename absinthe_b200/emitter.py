@@ -40,6 +40,8 @@ DEFAULTS = {
     "BLOCK": (1, 1),             # (RJ, RK): points per thread along j and k
     "SHUFFLE": False,            # inlined intermediates at i-offsets come from neighbour lanes
     "BRANCH": False,             # expensive ?: arms become real (warp-coherent) branches
+    "STREAM_K": False,           # walk a tile column plane by plane through a ring of k-planes
+    "PREFETCH": 2,               # STREAM_K: input planes in flight beyond the ones being read
 }
 FRONT_SLACK = 16                 # doubles before the first box (halo lanes of a warp read below it)
 MAX_BOX = 256                    # TMA box limit per dimension
@@ -176,6 +178,25 @@ class GroupPlan:
             self.load = "ldg"              # TMA needs 16-byte global strides
         self.stages = opts["STAGES"] if self.load == "tma" else 1
         self.threads = opts["THREADS"]
+        self.stream = bool(opts["STREAM_K"]) and self.load == "tma" and self.block[2] == 1
+        if self.stream:
+            # k-streaming: one work item is a (bx, by) column over the whole k-range of its tile.  Plane g
+            # of every staged input travels together in ring slot g mod R; a phase whose results are read
+            # up to d planes ahead runs d planes ahead of the output plane.
+            self.prefetch = max(1, int(opts["PREFETCH"]))
+            self.stages = self.prefetch + 1          # barrier slots: one full/empty pair per step in flight
+            self.kmin = min(ph["BOX"][2][0] - ph["BOX"][2][1] for ph in self.phase_list)
+            # planes of an input alive at output plane kk: [kk + lo, kk + hi], from the k-offsets its
+            # consumers use and how far ahead of kk each consuming phase runs
+            self.win = {}
+            for ph in self.phase_list:
+                ahead = ph["BOX"][2][1]
+                for m in ph["NAMES"]:
+                    for field, box in self.closure[m].items():
+                        if field in self.staged:
+                            lo, hi = ahead + box[2][0], ahead + box[2][1]
+                            old = self.win.get(field, (lo, hi))
+                            self.win[field] = (min(old[0], lo), max(old[1], hi))
         self.fuse_halo = bool(opts["FUSE_HALO"]) and all(s >= 2 * h for s, h in zip(dims, self.H))
         self.B = self._choose_subtile()
         self.nsub = tuple(A.ceil_div(t, b) for t, b in zip(self.T, self.B))
@@ -216,13 +237,15 @@ class GroupPlan:
                 keep.append(n)
         self.in_smem = keep
         centre_only = [n for n in self.inputs if self.reach[n] == A.ZERO_BOX]
-        direct = self.opts["DIRECT"]
+        direct = "none" if self.opts["STREAM_K"] else self.opts["DIRECT"]
         self.direct = self._select("all" if direct == "auto" else direct, centre_only)
         self.staged = [n for n in self.inputs if n not in self.direct]
 
     # -- shared-memory planning -----------------------------------------------------------
-    def _box_dims(self, B, box, even_x=False):
+    def _box_dims(self, B, box, even_x=False, planes=False):
         d = [B[a] + box[a][1] - box[a][0] for a in range(3)]
+        if planes and getattr(self, "stream", False):
+            d[2] = 1
         if even_x and self.load == "tma":
             # TMA wants the box to start on a 16-byte boundary (an even fp64 column, measured:
             # odd start columns raise "illegal instruction") and its inner extent to be a
@@ -234,21 +257,32 @@ class GroupPlan:
         """Doubles a thread block may read past a box when its RJ x RK block overhangs the range."""
         worst = 0
         for name in self.staged + self.in_smem:
-            d = self._box_dims(B, self.reach[name], even_x=name in self.staged)
+            d = self._box_dims(B, self.reach[name], even_x=name in self.staged, planes=True)
             worst = max(worst, (self.block[1] - 1) * d[0] + (self.block[2] - 1) * d[0] * d[1])
         if self.opts["SHUFFLE"]:
             worst += 48                     # lanes of the last warp segment past the end of a row
         return _round_up(worst, ALIGN_DOUBLES)
 
+    def _temp_depth(self, name):
+        """Planes of a streamed intermediate kept alive: its k-extent plus one (see template)."""
+        return self.reach[name][2][1] - self.reach[name][2][0] + 2
+
+    def _ring(self, name):
+        """Planes of a streamed input resident at once: its k-window plus the prefetch distance."""
+        lo, hi = self.win[name]
+        return hi - lo + 1 + self.prefetch
+
     def _footprint(self, B):
         total = 0
         for name in self.staged:
-            d = self._box_dims(B, self.reach[name], even_x=True)
-            total += self.stages * _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+            d = self._box_dims(B, self.reach[name], even_x=True, planes=True)
+            depth = self._ring(name) if self.stream else self.stages
+            total += depth * _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
         for name in self.in_smem:
-            d = self._box_dims(B, self.reach[name])
-            total += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
-        return (total + self._slack(B) + FRONT_SLACK) * 8 + 128
+            d = self._box_dims(B, self.reach[name], planes=True)
+            depth = self._temp_depth(name) if self.stream else 1
+            total += depth * _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+        return (total + self._slack(B) + FRONT_SLACK) * 8 + 128 + 16 * self.stages
 
     def _cost(self, B):
         """Work per useful point of a sub-tile ``B``: staged cells (short rows cost extra: every
@@ -257,16 +291,18 @@ class GroupPlan:
         row_slack, item_overhead = 12, 3000
         moved = item_overhead
         for name in self.staged:
-            d = self._box_dims(B, self.reach[name], even_x=True)
+            d = self._box_dims(B, self.reach[name], even_x=True, planes=True)
             moved += (d[0] + row_slack) * d[1] * d[2]
         for name in self.materialised:
-            d = self._box_dims(B, self.reach[name])
+            d = self._box_dims(B, self.reach[name], planes=True)
             moved += d[0] * d[1] * d[2] * 0.25 * len(self.closure[name])
-        return moved / float(B[0] * B[1] * B[2])
+        return moved / float(B[0] * B[1] * (1 if self.stream else B[2]))
 
     def _choose_subtile(self):
         if self.opts["SUBTILE"]:
             B = tuple(min(b, t) for b, t in zip(self.opts["SUBTILE"], self.T))
+            if self.stream:
+                B = (B[0], B[1], self.T[2])
             assert self._footprint(B) <= SMEM_LIMIT, "SUBTILE does not fit in shared memory"
             return B
         widest = [0, 0, 0]
@@ -281,8 +317,8 @@ class GroupPlan:
             for by in _splits(self.T[1]):
                 if by + widest[1] > MAX_BOX:
                     continue
-                for bz in _splits(self.T[2]):
-                    if bz + widest[2] > MAX_BOX:
+                for bz in ([self.T[2]] if self.stream else _splits(self.T[2])):
+                    if not self.stream and bz + widest[2] > MAX_BOX:
                         continue
                     B = (bx, by, bz)
                     # a thread's RJ x RK block should not overhang the sub-tile
@@ -309,31 +345,45 @@ class GroupPlan:
             if name in self.direct:
                 continue
             box = self.reach[name]
-            d = self._box_dims(B, box, even_x=True)
+            d = self._box_dims(B, box, even_x=True, planes=True)
             lo = [box[a][0] for a in range(3)]
             self.input_plan.append({
                 "NAME": name, "INDEX": n, "MAP": len(self.input_plan), "LO": lo, "DIM": d, "OFFSET": cursor,
                 "ROW": d[0], "PLANE": d[0] * d[1], "CELLS": d[0] * d[1] * d[2],
                 # pointer bias so that relative (i, j, k) index the box directly
-                "BIAS": cursor - (lo[0] + lo[1] * d[0] + lo[2] * d[0] * d[1]),
+                "BIAS": cursor - (lo[0] + lo[1] * d[0] + (0 if self.stream else lo[2] * d[0] * d[1])),
             })
-            cursor += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+            slot = _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+            if self.stream:
+                ring = self._ring(name)
+                self.input_plan[-1].update(RING=ring, SLOT=slot, WK=self.win[name][1] - self.win[name][0],
+                                           LOKX=self.win[name][0])
+                cursor += ring * slot
+            else:
+                cursor += slot
         self.stage_doubles = cursor
         self.stage_bytes = sum(p["CELLS"] for p in self.input_plan) * 8
-        cursor = self.stages * self.stage_doubles
+        if self.stream:
+            self.first_bytes = sum(p["CELLS"] * (p["WK"] + 1) for p in self.input_plan) * 8
+        else:
+            cursor = self.stages * self.stage_doubles
         self.temp_plan = {}
         for name in self.in_smem:
             box = self.reach[name]
-            d = self._box_dims(B, box)
+            d = self._box_dims(B, box, planes=True)
             lo = [box[a][0] for a in range(3)]
+            depth = self._temp_depth(name) if self.stream else 1
+            slot = _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
             self.temp_plan[name] = {
                 "NAME": name, "LO": lo, "DIM": d, "OFFSET": cursor, "ROW": d[0], "PLANE": d[0] * d[1],
-                "BIAS": cursor - (lo[0] + lo[1] * d[0] + lo[2] * d[0] * d[1]),
+                "BIAS": cursor - (lo[0] + lo[1] * d[0] + (0 if self.stream else lo[2] * d[0] * d[1])),
+                "DEPTH": depth, "SLOT": slot,
             }
-            cursor += _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
+            cursor += depth * slot
         cursor += self._slack(B) + self.front
         self.barrier_offset = cursor * 8
         self.smem_bytes = cursor * 8 + 16 * max(self.stages, 1) + 48
+
         self.launch_threads = self.threads + (32 if self.load == "tma" else 0)
         assert self.smem_bytes <= SMEM_LIMIT, "shared-memory plan exceeds the sm_100a limit"
         # parameter block: tensor maps (128 B each, 64-byte aligned), pointers, tile control
@@ -402,9 +452,17 @@ class GroupPlan:
         shuffle = bool(self.opts["SHUFFLE"])
         lines, memo, lanes = [], {}, {}
         same_phase = set(phase["NAMES"])
+        planes = phase.setdefault("PLANES", set())     # (kind, field, k-offset) plane pointers needed
 
         def const_index(off, row, plane):
-            return off[0] + off[1] * row + off[2] * plane
+            return off[0] + off[1] * row + (0 if self.stream else off[2] * plane)
+
+        def base(kind, field, off):
+            """Name of the array a load goes through: one pointer per k-plane when streaming."""
+            if not self.stream:
+                return "%s_%s" % (kind, field)
+            planes.add((kind, field, off[2]))
+            return "%s_%s_k%s" % (kind, field, ("m%d" % -off[2]) if off[2] < 0 else str(off[2]))
 
         def value(field, off):
             """C expression of ``field`` at block-relative offset ``off``."""
@@ -415,8 +473,8 @@ class GroupPlan:
             if field in staged:
                 p = staged[field]
                 var = "l_" + tag
-                lines.append("const double %s = in_%s[b_%s + (%d)];" % (
-                    var, field, field, const_index(off, p["ROW"], p["PLANE"])))
+                lines.append("const double %s = %s[b_%s + (%d)];" % (
+                    var, base("in", field, off), field, const_index(off, p["ROW"], p["PLANE"])))
                 lanes[var] = (0, 31)
             elif field in self.direct:
                 var = "l_" + tag
@@ -427,8 +485,8 @@ class GroupPlan:
             elif field in self.temp_plan and field not in same_phase:
                 p = self.temp_plan[field]
                 var = "l_" + tag
-                lines.append("const double %s = tmp_%s[b_%s + (%d)];" % (
-                    var, field, field, const_index(off, p["ROW"], p["PLANE"])))
+                lines.append("const double %s = %s[b_%s + (%d)];" % (
+                    var, base("tmp", field, off), field, const_index(off, p["ROW"], p["PLANE"])))
                 lanes[var] = (0, 31)
             elif field in same_phase:
                 raise AssertionError("phase split missed a dependence on " + field)
@@ -485,7 +543,7 @@ class GroupPlan:
             box = phase["BOX"]
             lo = [box[a][0] for a in range(3)]
             hi = [box[a][1] for a in range(3)]
-            dim = self._box_dims(self.B, box)
+            dim = self._box_dims(self.B, box, planes=True)
             blocks = [dim[0], A.ceil_div(dim[1], self.block[1]), A.ceil_div(dim[2], self.block[2])]
             reads = set()
             for name in phase["NAMES"]:
@@ -497,7 +555,16 @@ class GroupPlan:
             lines, stores, lanes = self._phase_body(phase)
             useful = lanes[1] - lanes[0] + 1
             nseg = A.ceil_div(dim[0], useful)
+            pointers = []
+            if self.stream:
+                wanted = set(phase["PLANES"]) | {("tmp", n, 0) for n in phase["NAMES"] if n in self.temp_plan}
+                staged = {p["NAME"]: p for p in self.input_plan}
+                for kind, field, c in sorted(wanted):
+                    plan = staged[field] if kind == "in" else self.temp_plan[field]
+                    pointers.append({"KIND": kind, "FIELD": field, "OFF": c, "PLAN": plan,
+                                     "NAME": "%s_%s_k%s" % (kind, field, ("m%d" % -c) if c < 0 else str(c))})
             out.append({
+                "D": hi[2], "KLO": lo[2], "POINTERS": pointers,
                 "SHUFFLE": bool(self.opts["SHUFFLE"]), "LANES": lanes, "USEFUL": useful, "NSEG": nseg,
                 "TASKS": nseg * blocks[1] * blocks[2],
                 "NAMES": phase["NAMES"], "LO": lo, "HI": hi, "DIM": dim, "BLOCKS": blocks,
@@ -529,6 +596,8 @@ class GroupPlan:
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
             "BLOCK": self.block, "FUSE_HALO": self.fuse_halo, "FRONT": self.front,
             "WARPS": self.threads // 32, "LAUNCH_THREADS": self.launch_threads,
+            "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
+            "FIRST_BYTES": getattr(self, "first_bytes", 0), "NB": self.stages,
         }
 
 

@@ -32,6 +32,10 @@ OPTIONS = [
     ("shuffle", {"INLINE": "all", "SHUFFLE": True, "FUSE_HALO": True}),
     ("shuffle-block4x2", {"INLINE": "all", "SHUFFLE": True, "BLOCK": (4, 2), "DIRECT": "auto", "THREADS": 128}),
     ("branch", {"INLINE": "all", "BRANCH": True, "BLOCK": (2, 1), "FUSE_HALO": True}),
+    ("stream-k", {"STREAM_K": True}),
+    ("stream-k-inline", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "PREFETCH": 1}),
+    ("stream-k-shuffle", {"STREAM_K": True, "INLINE": "all", "BLOCK": (3, 1), "SHUFFLE": True, "FUSE_HALO": True,
+                          "PREFETCH": 3, "THREADS": 128}),
 ]
 PARTIAL_INLINE = {"diffusion": ["ufli", "uflj", "vfli", "vflj", "wfli", "wflj", "ppfli", "ppflj"],
                   "advection": ["uatu", "vatu"], "fastwaves": ["ppgk", "ppgc", "udc"]}
@@ -51,6 +55,8 @@ def test_partial_inlining_matches_oracle(launcher_lib, name, program):
     program["CUDA"] = {"INLINE": PARTIAL_INLINE[program["NAME"]], "BLOCK": (2, 2), "FUSE_HALO": True}
     assert_bit_exact(program)
     program["CUDA"]["SHUFFLE"] = True
+    assert_bit_exact(program)
+    program["CUDA"].update(STREAM_K=True, BLOCK=(2, 1))
     assert_bit_exact(program)
 
 
