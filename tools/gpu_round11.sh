@@ -1,0 +1,5 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 2400 python tools/autotune.py --kernel fastwaves --assignment 000000000 --tiles 128x8x80,256x8x80,256x4x80,128x16x80,512x4x80,256x8x40 --budgets 110,220 --threads 256,384,512 --runs 3 \
+  --sweep "{\"INLINE\":[\"all\"],\"BLOCK\":[[1,1],[2,1],[4,1]],\"FUSE_HALO\":[true],\"SHUFFLE\":[true,false],\"STREAM_K\":[true],\"PREFETCH\":[1,2,3]}" \
+  --out gpurun_out/tune_fastwaves_stream.json > gpurun_out/tune_fastwaves_stream.log 2>&1; grep BEST gpurun_out/tune_fastwaves_stream.log
