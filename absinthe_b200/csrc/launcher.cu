@@ -794,7 +794,8 @@ int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inpu
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = absinthe_variant_field_bytes(v);
     for (size_t n = 0; n < v->inputs.size(); ++n)
-        RT(cudaMemcpyAsync(v->fields[v->inputs[n]].ptr, h_inputs[n], bytes, cudaMemcpyHostToDevice, s));
+        if (h_inputs[n])   // a null entry keeps the device-resident field (constants uploaded once)
+            RT(cudaMemcpyAsync(v->fields[v->inputs[n]].ptr, h_inputs[n], bytes, cudaMemcpyHostToDevice, s));
     if ((rc = absinthe_variant_apply(v, s))) return rc;
     for (size_t n = 0; n < v->outputs.size(); ++n)
         RT(cudaMemcpyAsync(h_outputs[n], v->fields[v->outputs[n]].ptr, bytes, cudaMemcpyDeviceToHost, s));
@@ -816,7 +817,8 @@ int absinthe_variant_apply_host_async(absinthe_variant* v, const double* const* 
     }
     const size_t bytes = absinthe_variant_field_bytes(v);
     for (size_t n = 0; n < v->inputs.size(); ++n)
-        RT(cudaMemcpyAsync(v->fields[v->inputs[n]].ptr, h_inputs[n], bytes, cudaMemcpyHostToDevice, v->h2d_stream));
+        if (h_inputs[n])
+            RT(cudaMemcpyAsync(v->fields[v->inputs[n]].ptr, h_inputs[n], bytes, cudaMemcpyHostToDevice, v->h2d_stream));
     RT(cudaEventRecord(v->ev_in, v->h2d_stream));
     RT(cudaStreamWaitEvent(s, v->ev_in, 0));
     if ((rc = absinthe_variant_apply(v, s))) return rc;

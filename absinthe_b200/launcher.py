@@ -218,7 +218,8 @@ class Variant:
         """End to end with HOST (pinned) tensors: H2D, apply, D2H.  ``wait=False`` returns while the
         copies are in flight on the variant's private copy streams (finish with ``wait_host``)."""
         fn = self.lib.absinthe_variant_apply_host if wait else self.lib.absinthe_variant_apply_host_async
-        check(self.lib, fn(self.handle, _pointer_array([t.data_ptr() for t in host_inputs]),
+        # ``None`` entries keep the device-resident field (constants bound once)
+        check(self.lib, fn(self.handle, _pointer_array([0 if t is None else t.data_ptr() for t in host_inputs]),
                            _pointer_array([t.data_ptr() for t in host_outputs]), _stream_handle(stream)),
               "apply_host")
         self._host = (host_inputs, host_outputs)

@@ -353,9 +353,14 @@ def run_gpu_arm(args):
     if world == 1 or True:
         e2e_steps = max(1, min(args.steps, 3))
         host = []
-        for item in variants:
+        constants = {}
+        for (name, program), item in zip(workload_programs(), variants):
             v = item["v"]
-            hin = [t.cpu().pin_memory() for t in item["ins"]]
+            # the program's CONSTANTS (mask; wgtfac, hhl, rho, dzdx, dzdy) stay resident on the device as
+            # bound; every step uploads the fields that change from step to step and downloads all outputs
+            const = [n for n in v.inputs if n in program.get("CONSTANTS", [])]
+            constants[name] = const
+            hin = [None if n in const else t.cpu().pin_memory() for n, t in zip(v.inputs, item["ins"])]
             hout = [torch.empty(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
             host.append((v, hin, hout))
         torch.cuda.synchronize()
@@ -373,11 +378,11 @@ def run_gpu_arm(args):
             t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
-        h2d = sum(len(hin) for _, hin, _ in host) * host[0][0].field_bytes
+        h2d = sum(sum(1 for t in hin if t is not None) for _, hin, _ in host) * host[0][0].field_bytes
         d2h = sum(len(hout) for _, _, hout in host) * host[0][0].field_bytes
         e2e = {"value": round(2 * points * world / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpoints/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 2),
-               "steps": e2e_steps, "api": "Variant.apply_host(wait=False) + wait_host (absinthe_variant_apply_host_async)"}
+               "steps": e2e_steps, "constants_resident": constants, "api": "Variant.apply_host(wait=False) + wait_host (absinthe_variant_apply_host_async)"}
 
     if rank == 0:
         line = {

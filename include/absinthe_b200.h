@@ -101,7 +101,9 @@ int absinthe_variant_run(absinthe_variant* v, void* stream, int runs, int flush,
                          float* total_ms, float* halo_ms);
 
 /* End-to-end with HOST buffers: H2D copy of every input, one application, D2H copy of every
- * output, synchronised on return.  h_inputs must have periodic halos. */
+ * output, synchronised on return.  h_inputs must have periodic halos.  A NULL entry of h_inputs
+ * skips that copy and uses the field as it is on the device (the program's CONSTANTS -- mask,
+ * wgtfac, hhl, ... -- are uploaded once at bind time and not per step). */
 int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inputs,
                                 double* const* h_outputs, void* stream);
 

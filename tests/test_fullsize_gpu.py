@@ -127,4 +127,11 @@ def test_host_path_matches_device_path(launcher_lib):
     v.wait_host()
     for name, t in zip(v.outputs, host_out):
         assert torch.equal(t, want[name].cpu()), name
+    # constants stay resident: a None entry skips the upload and uses the field on the device
+    for t in host_out:
+        t.zero_()
+    resident = ["wgtfac", "hhl", "rho", "dzdx", "dzdy"]
+    v.apply_host([None if n in resident else h for n, h in zip(v.inputs, host_in)], host_out)
+    for name, t in zip(v.outputs, host_out):
+        assert torch.equal(t, want[name].cpu()), name
     v.close()
