@@ -40,6 +40,8 @@ DEFAULTS = {
     "BLOCK": (1, 1),             # (RJ, RK): points per thread along j and k
     "SHUFFLE": False,            # inlined intermediates at i-offsets come from neighbour lanes
     "BRANCH": False,             # expensive ?: arms become real (warp-coherent) branches
+    "STORE_CS": False,           # outputs written with the evict-first (streaming) cache hint
+    "L2_ONCE": False,            # centre-only inputs are staged with an L2 evict-first policy
     "STREAM_K": False,           # walk a tile column plane by plane through a ring of k-planes
     "PREFETCH": 2,               # STREAM_K: input planes in flight beyond the ones being read
 }
@@ -352,6 +354,7 @@ class GroupPlan:
                 "ROW": d[0], "PLANE": d[0] * d[1], "CELLS": d[0] * d[1] * d[2],
                 # pointer bias so that relative (i, j, k) index the box directly
                 "BIAS": cursor - (lo[0] + lo[1] * d[0] + (0 if self.stream else lo[2] * d[0] * d[1])),
+                "ONCE": bool(self.opts["L2_ONCE"]) and box == A.ZERO_BOX,
             })
             slot = _round_up(d[0] * d[1] * d[2], ALIGN_DOUBLES)
             if self.stream:
@@ -596,7 +599,7 @@ class GroupPlan:
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
             "BLOCK": self.block, "FUSE_HALO": self.fuse_halo, "FRONT": self.front,
             "WARPS": self.threads // 32, "LAUNCH_THREADS": self.launch_threads,
-            "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
+            "STREAM_STORES": bool(self.opts["STORE_CS"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
             "FIRST_BYTES": getattr(self, "first_bytes", 0), "NB": self.stages,
         }
 
