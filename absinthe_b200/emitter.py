@@ -42,6 +42,7 @@ DEFAULTS = {
     "BRANCH": False,             # expensive ?: arms become real (warp-coherent) branches
     "STORE_CS": False,           # outputs written with the evict-first (streaming) cache hint
     "L2_ONCE": False,            # centre-only inputs are staged with an L2 evict-first policy
+    "L2_PREFETCH": 0,            # work items whose boxes are prefetched into L2 ahead of the ring
     "STREAM_K": False,           # walk a tile column plane by plane through a ring of k-planes
     "PREFETCH": 2,               # STREAM_K: input planes in flight beyond the ones being read
 }
@@ -599,7 +600,7 @@ class GroupPlan:
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
             "BLOCK": self.block, "FUSE_HALO": self.fuse_halo, "FRONT": self.front,
             "WARPS": self.threads // 32, "LAUNCH_THREADS": self.launch_threads,
-            "STREAM_STORES": bool(self.opts["STORE_CS"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
+            "STREAM_STORES": bool(self.opts["STORE_CS"]), "L2_PREFETCH": int(self.opts["L2_PREFETCH"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
             "FIRST_BYTES": getattr(self, "first_bytes", 0), "NB": self.stages,
         }
 

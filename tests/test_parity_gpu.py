@@ -32,7 +32,8 @@ OPTIONS = [
     ("shuffle", {"INLINE": "all", "SHUFFLE": True, "FUSE_HALO": True}),
     ("shuffle-block4x2", {"INLINE": "all", "SHUFFLE": True, "BLOCK": (4, 2), "DIRECT": "auto", "THREADS": 128}),
     ("branch", {"INLINE": "all", "BRANCH": True, "BLOCK": (2, 1), "FUSE_HALO": True}),
-    ("cache-hints", {"INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "STORE_CS": True, "L2_ONCE": True}),
+    ("cache-hints", {"INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "STORE_CS": True, "L2_ONCE": True,
+                     "L2_PREFETCH": 3}),
     ("stream-k", {"STREAM_K": True}),
     ("stream-k-inline", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "PREFETCH": 1}),
     ("stream-k-shuffle", {"STREAM_K": True, "INLINE": "all", "BLOCK": (3, 1), "SHUFFLE": True, "FUSE_HALO": True,
