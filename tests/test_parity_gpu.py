@@ -101,3 +101,35 @@ def test_training_protocol_matches_oracle_on_selected_tiles(launcher_lib, family
         assert np.array_equal(got[mask], want[mask]), name
         assert np.all(got[~mask] == -7.0), name
     v.close()
+
+
+def _shipped_cases(per_kernel=5):
+    """Fusion groupings of variants the reference ships estimates for (names like
+    ``diffusion-0-0-1-1-...-mz``): the grouping is in the name, the tile counts are not pinned
+    (SURVEY.md section 8c), so deterministic pseudo-random counts are used."""
+    import json
+    import os
+    import random
+    names = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "shipped_variants.json")))
+    rng = random.Random(2019)
+    cases = []
+    for kernel, variants in sorted(names.items()):
+        seq = P.KERNELS[kernel][1]()
+        grouped = [v for v in variants if v.startswith(kernel + "-")]
+        for name in rng.sample(grouped, per_kernel):
+            digits = [int(t) for t in name.split("-")[1:1 + len(seq)]]
+            groups = P.split_sequence(seq, digits)
+            tiles = [(rng.choice([1, 2, 3, 5]), rng.choice([1, 2, 4, 7]), rng.choice([1, 2, 3])) for _ in groups]
+            cases.append((name, P.make_program(kernel, groups, tiles, domain=(40, 28, 12), variant=name)))
+    return cases
+
+
+SHIPPED = _shipped_cases()
+
+
+@pytest.mark.parametrize("name,program", SHIPPED, ids=[c[0] for c in SHIPPED])
+def test_shipped_variant_groupings_match_oracle(launcher_lib, name, program):
+    assert_bit_exact(program)
+    tuned = P.clone(program)
+    tuned["CUDA"] = {"INLINE": "all", "BLOCK": (2, 1), "SHUFFLE": True, "FUSE_HALO": True}
+    assert_bit_exact(tuned)

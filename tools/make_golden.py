@@ -158,10 +158,21 @@ def parse_fixture():
     return out
 
 
+def shipped_variants():
+    """VAR names of the implementation variants the reference ships estimates for (*/estimates.csv)."""
+    import csv
+    out = {}
+    for kernel in ("diffusion", "advection", "fastwaves"):
+        with open(os.path.join(REFERENCE, kernel, "estimates.csv")) as handle:
+            out[kernel] = sorted(r["VAR"] for r in csv.DictReader(handle))
+    return out
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     for name, fn in (("stencil_fingerprints", stencil_fingerprints), ("analysis", analysis_fixtures),
-                     ("parse_results", parse_fixture), ("reference_digests", reference_digests)):
+                     ("parse_results", parse_fixture), ("shipped_variants", shipped_variants),
+                     ("reference_digests", reference_digests)):
         with open(os.path.join(GOLDEN, name + ".json"), "w") as handle:
             json.dump(fn(), handle, indent=1, sort_keys=True)
         print("wrote", name)

@@ -24,6 +24,9 @@ def main():
         q = P.clone(program); q["CUDA"] = {"INLINE": T.PARTIAL_INLINE[program["NAME"]], "BLOCK": (2, 2), "FUSE_HALO": True}; jobs.append(q)
         q = P.clone(q); q["CUDA"]["SHUFFLE"] = True; jobs.append(q)
         q = P.clone(q); q["CUDA"].update(STREAM_K=True, BLOCK=(2, 1)); jobs.append(q)
+    for _, program in T.SHIPPED:
+        jobs.append(P.clone(program))
+        q = P.clone(program); q["CUDA"] = {"INLINE": "all", "BLOCK": (2, 1), "SHUFFLE": True, "FUSE_HALO": True}; jobs.append(q)
     with ProcessPoolExecutor(max_workers=os.cpu_count()) as pool:
         errors = [e for e in pool.map(build, jobs) if e]
     print(len(jobs), "variants,", len(errors), "failures")
