@@ -7,18 +7,21 @@ group, everything ``template_tiling.cu`` needs to render one sm_100a kernel:
   truncating offset ``O = -(T*N - S)/2`` (ref template_tiling.cpp:228-233),
   tiles enumerated x-fastest (ref :240-242).  One tile is one CTA's unit of
   work; CTAs are persistent and take tiles ``blockIdx.x, +gridDim.x, ...``.
-* a *sub-tile* ``B <= T``: the box whose haloed inputs (two TMA stages) and
-  intermediates fit in shared memory.  A tile is walked as ``ceil(T/B)``
-  sub-tiles with overlapped (redundant) evaluation exactly like the tiles
-  themselves, so results do not depend on ``B``.
+* a *sub-tile* ``B <= T``: the box whose haloed inputs (a ring of 2-4 TMA
+  stages) and intermediates fit in shared memory.  A tile is walked as
+  ``ceil(T/B)`` sub-tiles with overlapped (redundant) evaluation exactly like
+  the tiles themselves, so results do not depend on ``B``.  With ``STREAM_K``
+  the sub-tile is a column walked plane by plane through rings of k-planes.
 * per input: the haloed box to stage (``LOOPS (+) OFFSETS`` of its consumers,
   what the reference's analyzer calls ``accesses``, ref stencil_analyzer.py:137-142),
   its shared-memory offset and strides, its tensor-map box.
-* per stencil ("pass"): the evaluation box (tile grown by ``LOOPS``), where
-  the result goes (shared-memory intermediate and/or global output) and the
-  stencil text with every ``field(i+a,j+b,k+c)`` access rewritten to an
-  indexed load -- the expression text between accesses is untouched, so
-  operand order is the reference's.
+* per *phase* (materialised stencils of equal box and dependency level): the
+  evaluation box (tile grown by ``LOOPS``), where results go (shared-memory
+  intermediate and/or global output) and straight-line code for a thread's
+  ``1 x RJ x RK`` block of points in which every ``field(i+a,j+b,k+c)`` access
+  is a memoised load, an inlined re-evaluation or a warp shuffle -- the
+  expression text between accesses is untouched, so operand order is the
+  reference's.
 
 The plan also yields the launcher descriptor (``descriptor_text``): fields,
 kernels, launch shapes, parameter-block layout, halo lists.

@@ -350,7 +350,7 @@ def run_gpu_arm(args):
     # end to end through the public API with HOST buffers (pinned), copies inside the timed region
     e2e = None
     launches = sum(item["v"].launches for item in variants) * args.steps
-    if world == 1 or True:
+    if True:
         e2e_steps = max(1, min(args.steps, 6))
         host = []
         constants = {}
