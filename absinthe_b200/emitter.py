@@ -45,6 +45,7 @@ DEFAULTS = {
     "BRANCH": False,             # expensive ?: arms become real (warp-coherent) branches
     "STORE_CS": False,           # outputs written with the evict-first (streaming) cache hint
     "L2_ONCE": False,            # centre-only inputs are staged with an L2 evict-first policy
+    "WAIT_SLEEP": 0,             # ns a starved consumer backs off between mbarrier polls
     "L2_PREFETCH": 0,            # work items whose boxes are prefetched into L2 ahead of the ring
     "STREAM_K": False,           # walk a tile column plane by plane through a ring of k-planes
     "PREFETCH": 2,               # STREAM_K: input planes in flight beyond the ones being read
@@ -631,7 +632,8 @@ class Plan:
         p = self.program
         ctx = {k: p[k] for k in ("X", "Y", "Z", "HX", "HY", "HZ")}
         ctx.update(VARIANT=p.get("VARIANT", p.get("NAME", "")), GROUPS=[g.context() for g in self.groups],
-                   ANY_TMA=any(g.load == "tma" for g in self.groups), FMAD=self.opts["FMAD"])
+                   ANY_TMA=any(g.load == "tma" for g in self.groups), FMAD=self.opts["FMAD"],
+                   WAIT_SLEEP=int(self.opts["WAIT_SLEEP"]))
         return ctx
 
     def nvcc_flags(self):
