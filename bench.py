@@ -228,7 +228,8 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"       # keep NCCL's version banner off stdout (one JSON line only)
+        # keep NCCL's version banner off stdout (rank 0 prints exactly one JSON line)
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/absinthe_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     if local == 0:                                 # one rank builds, the others wait for the cache
