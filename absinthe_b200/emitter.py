@@ -542,6 +542,8 @@ class GroupPlan:
                     stores.append((name, rj, rk, var))
                     first, last = max(first, lanes[var][0]), min(last, lanes[var][1])
         assert first <= last, "shuffle chain longer than a warp"
+        # lanes left of the first owning one read below the start of a staged row: covered by FRONT_SLACK
+        assert first + max(self.H) + 1 <= FRONT_SLACK, "shuffle chain reaches below the front slack"
         return lines, stores, (first, last)
 
     def passes(self):
