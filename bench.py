@@ -105,7 +105,7 @@ class ClockSampler(threading.Thread):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE, text=True)
+                 "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
         except Exception:
