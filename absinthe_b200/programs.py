@@ -5,7 +5,7 @@ A *program* is the plain dict the reference's drivers assemble
 fitcache.py:61-85, fitddr.py:127-156) and hand to ``generate_code``.  The
 schema is kept verbatim; only the machine-model numbers
 differ because they describe a B200 instead of the authors' 4-core CPU
-(see ``model.py``).
+(see ``fit.py``).
 """
 
 from copy import deepcopy
@@ -19,7 +19,7 @@ B200_SMEM_PER_CTA = 227 * 1024
 
 # Analytical-model parameters.  MEMORY/CACHE start from the reference's CPU
 # fit (ref diffusion.py:72-73) and are replaced by the GPU fit that
-# ``fitcache.py`` / ``fitddr.py`` + ``absinthe_b200.fit`` produce (model.py).
+# ``fitcache.py`` / ``fitddr.py`` + ``absinthe_b200.fit`` produce.
 CPU_MEMORY = {"RW BODY": -2.23e-7, "ST BODY": 5.71e-7, "RW PEEL": -1.25e-6, "ST PEEL": 5.25e-6}
 CPU_CACHE = {"BODY": 9.44e-8, "PEEL": 9.95e-7}
 
