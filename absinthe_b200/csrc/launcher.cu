@@ -115,6 +115,7 @@ struct Geometry {
 };
 
 constexpr int kMaxHaloFields = 16;
+constexpr int kHostDepth = 2;        // asynchronous host steps one variant keeps in flight
 struct FieldList {
     double* ptr[kMaxHaloFields];
     int count;
@@ -313,7 +314,9 @@ struct absinthe_variant {
     cudaGraphExec_t graph = nullptr;
     cudaStream_t graph_stream = nullptr;
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
-    cudaEvent_t ev_in = nullptr, ev_done = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_in = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_out[kHostDepth] = {};                  // outputs of async host step n are in ev_out[n % depth]
+    unsigned long long host_issued = 0, host_waited = 0;  // async host steps enqueued / waited for
     std::vector<cudaEvent_t> events;
 };
 
@@ -558,7 +561,9 @@ void absinthe_variant_free(absinthe_variant* v) {
     if (v->graph_stream) cudaStreamDestroy(v->graph_stream);
     if (v->h2d_stream) cudaStreamDestroy(v->h2d_stream);
     if (v->d2h_stream) cudaStreamDestroy(v->d2h_stream);
-    for (cudaEvent_t e : {v->ev_in, v->ev_done, v->ev_out})
+    for (cudaEvent_t e : {v->ev_in, v->ev_done})
+        if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : v->ev_out)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : v->events) cudaEventDestroy(e);
     for (Field& f : v->fields)
@@ -787,10 +792,21 @@ int absinthe_variant_run(absinthe_variant* v, void* stream, int runs, int flush,
     return 0;
 }
 
+int absinthe_variant_wait_host(absinthe_variant* v) {
+    if (!v) return fail(-3, "null variant");
+    if (v->host_waited < v->host_issued) {
+        RT(cudaEventSynchronize(v->ev_out[v->host_waited % kHostDepth]));
+        ++v->host_waited;
+    }
+    return 0;
+}
+
 int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inputs,
                                 double* const* h_outputs, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    while (v->host_waited < v->host_issued)   // async steps still in flight use the same device fields
+        if ((rc = absinthe_variant_wait_host(v))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     const size_t bytes = absinthe_variant_field_bytes(v);
     for (size_t n = 0; n < v->inputs.size(); ++n)
@@ -807,32 +823,35 @@ int absinthe_variant_apply_host_async(absinthe_variant* v, const double* const* 
                                       double* const* h_outputs, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    if (v->host_issued - v->host_waited >= kHostDepth)
+        return fail(-6, "%d host steps already in flight: call absinthe_variant_wait_host first", kHostDepth);
     cudaStream_t s = (cudaStream_t)stream;
     if (!v->h2d_stream) {
         RT(cudaStreamCreateWithFlags(&v->h2d_stream, cudaStreamNonBlocking));
         RT(cudaStreamCreateWithFlags(&v->d2h_stream, cudaStreamNonBlocking));
         RT(cudaEventCreateWithFlags(&v->ev_in, cudaEventDisableTiming));
         RT(cudaEventCreateWithFlags(&v->ev_done, cudaEventDisableTiming));
-        RT(cudaEventCreateWithFlags(&v->ev_out, cudaEventDisableTiming));
+        for (cudaEvent_t& e : v->ev_out) RT(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     }
+    const bool chained = v->host_issued > 0;
     const size_t bytes = absinthe_variant_field_bytes(v);
+    // the upload may overwrite the device inputs as soon as the previous step's kernels have read them
+    // (ev_done still holds that step's record), i.e. while its outputs are still on their way to the host
+    if (chained) RT(cudaStreamWaitEvent(v->h2d_stream, v->ev_done, 0));
     for (size_t n = 0; n < v->inputs.size(); ++n)
         if (h_inputs[n])
             RT(cudaMemcpyAsync(v->fields[v->inputs[n]].ptr, h_inputs[n], bytes, cudaMemcpyHostToDevice, v->h2d_stream));
     RT(cudaEventRecord(v->ev_in, v->h2d_stream));
     RT(cudaStreamWaitEvent(s, v->ev_in, 0));
+    // ... and the kernels may overwrite the device outputs once the previous step's download has read them
+    if (chained) RT(cudaStreamWaitEvent(s, v->ev_out[(v->host_issued - 1) % kHostDepth], 0));
     if ((rc = absinthe_variant_apply(v, s))) return rc;
     RT(cudaEventRecord(v->ev_done, s));
     RT(cudaStreamWaitEvent(v->d2h_stream, v->ev_done, 0));
     for (size_t n = 0; n < v->outputs.size(); ++n)
         RT(cudaMemcpyAsync(h_outputs[n], v->fields[v->outputs[n]].ptr, bytes, cudaMemcpyDeviceToHost, v->d2h_stream));
-    RT(cudaEventRecord(v->ev_out, v->d2h_stream));
-    return 0;
-}
-
-int absinthe_variant_wait_host(absinthe_variant* v) {
-    if (!v) return fail(-3, "null variant");
-    if (v->ev_out) RT(cudaEventSynchronize(v->ev_out));
+    RT(cudaEventRecord(v->ev_out[v->host_issued % kHostDepth], v->d2h_stream));
+    ++v->host_issued;
     return 0;
 }
 

@@ -137,6 +137,7 @@ class Variant:
         self.field_bytes = self.lib.absinthe_variant_field_bytes(self.handle)
         self.points = self.X * self.Y * self.Z
         self._bound = None
+        self._host = []
 
     @classmethod
     def from_program(cls, program, template="template_tiling.cu", device=0):
@@ -216,13 +217,14 @@ class Variant:
 
     def apply_host(self, host_inputs, host_outputs, stream=None, wait=True):
         """End to end with HOST (pinned) tensors: H2D, apply, D2H.  ``wait=False`` returns while the
-        copies are in flight on the variant's private copy streams (finish with ``wait_host``)."""
+        copies are in flight on the variant's private copy streams; ``wait_host`` then blocks for the
+        oldest step in flight.  Two steps may be in flight (with their own host output tensors)."""
         fn = self.lib.absinthe_variant_apply_host if wait else self.lib.absinthe_variant_apply_host_async
         # ``None`` entries keep the device-resident field (constants bound once)
         check(self.lib, fn(self.handle, _pointer_array([0 if t is None else t.data_ptr() for t in host_inputs]),
                            _pointer_array([t.data_ptr() for t in host_outputs]), _stream_handle(stream)),
               "apply_host")
-        self._host = (host_inputs, host_outputs)
+        self._host = (self._host + [(host_inputs, host_outputs)])[-2:]   # keep the buffers of steps in flight alive
 
     def wait_host(self):
         check(self.lib, self.lib.absinthe_variant_wait_host(self.handle), "wait_host")

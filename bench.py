@@ -99,7 +99,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.window = index, [], None, [None, None, None]
 
     def run(self):
         try:
@@ -107,16 +107,25 @@ class ClockSampler(threading.Thread):
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
                  "--format=csv,noheader,nounits", "-lms", "20"], stdout=subprocess.PIPE, text=True)
             for line in self.proc.stdout:
-                self.rows.append([c.strip() for c in line.split(",")])
+                self.rows.append((time.monotonic(), [c.strip() for c in line.split(",")]))
         except Exception:
             pass
+
+    def mark(self, which):
+        """Host time stamps: 0 = start of the timed region, 1 = after its final synchronize, 2 = warm-up start."""
+        self.window[which] = time.monotonic()
 
     def stop(self):
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
         sm, reasons, sm_max = [], set(), None
-        for row in self.rows:
+        lo, hi, warm = self.window
+        timed = [row for t, row in self.rows if lo is not None and hi is not None and lo <= t <= hi + 0.02]
+        # a timed region shorter than a few sampling periods holds too few samples: then the warm-up steps
+        # that ran right before it (same kernels, same load) are counted too, and the line says so
+        window = "timed region" if len(timed) >= 3 else "warm-up + timed region"
+        for row in (timed if len(timed) >= 3 else [row for t, row in self.rows if warm is None or t >= warm]):
             try:
                 sm.append(float(row[0]))
                 sm_max = float(row[1])
@@ -128,7 +137,7 @@ class ClockSampler(threading.Thread):
                     reasons.add(name)
         busy = [c for c in sm if sm_max and c > 0.3 * sm_max] or sm
         return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": sm_max,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window, "period_ms": 20}
 
 
 def cpu_reference_time(name, steps, warmup):
@@ -209,6 +218,18 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def _available_host_bytes():
+    """MemAvailable of the box (0 when /proc/meminfo cannot be read: the caller then stays frugal)."""
+    try:
+        with open("/proc/meminfo") as handle:
+            for line in handle:
+                if line.startswith("MemAvailable:"):
+                    return int(line.split()[1]) * 1024
+    except OSError:
+        pass
+    return 0
+
+
 def workload_config(gpus):
     return {"workload": "diffusion+fastwaves fused sequences, %dx%dx%d fp64 per GPU, halo 3, periodic" % DOMAIN,
             "domain_per_gpu": list(DOMAIN), "decomposition": "j-slabs x%d" % gpus,
@@ -232,6 +253,8 @@ def run_gpu_arm(args):
         os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/absinthe_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    sampler = ClockSampler(local)                  # started early: nvidia-smi takes a while to come up
+    sampler.start()
     if local == 0:                                 # one rank builds, the others wait for the cache
         build_launcher()
         from absinthe_b200.generator import build_variant
@@ -288,9 +311,14 @@ def run_gpu_arm(args):
                     c.record()
                     record.append((item["name"], g, a, b, c))
 
-    sampler = ClockSampler(local)
-    sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    # the sampler was started before the variants were built; make sure nvidia-smi is delivering samples
+    # before the GPU work begins (at most 3 s), then W (>= 3) warm-up steps
+    wait_t0 = time.monotonic()
+    while not sampler.rows and time.monotonic() - wait_t0 < 3.0:
+        time.sleep(0.01)
+    warm = max(args.warmup, 3)
+    sampler.mark(2)
+    for _ in range(warm):
         step()
     torch.cuda.synchronize()
     if world > 1:
@@ -298,6 +326,7 @@ def run_gpu_arm(args):
     records = []
     start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
+    sampler.mark(0)
     start.record()
     for _ in range(args.steps):
         step(records)
@@ -307,6 +336,7 @@ def run_gpu_arm(args):
                 item["exchange"].wait(g)
     stop.record()
     torch.cuda.synchronize()
+    sampler.mark(1)
     elapsed_ms = start.elapsed_time(stop)
     clocks = sampler.stop()
     if world > 1:
@@ -352,9 +382,14 @@ def run_gpu_arm(args):
     e2e = None
     launches = sum(item["v"].launches for item in variants) * args.steps
     if True:
-        e2e_steps = max(1, min(args.steps, 6))
+        e2e_steps = max(1, min(args.steps, 10))
         host = []
         constants = {}
+        nfields = sum(len(item["v"].inputs) + 2 * len(item["v"].outputs) for item in variants)
+        local = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+        # two steps of a sequence in flight need their own host output buffers; fall back to one step in
+        # flight when the box could not pin that much memory for all its ranks
+        depth = 2 if _available_host_bytes() > 2 * local * nfields * variants[0]["v"].field_bytes else 1
         for (name, program), item in zip(workload_programs(), variants):
             v = item["v"]
             # the program's CONSTANTS (mask; wgtfac, hhl, rho, dzdx, dzdy) stay resident on the device as
@@ -362,38 +397,43 @@ def run_gpu_arm(args):
             const = [n for n in v.inputs if n in program.get("CONSTANTS", [])]
             constants[name] = const
             hin = [None if n in const else t.cpu().pin_memory() for n, t in zip(v.inputs, item["ins"])]
-            hout = [torch.empty(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
-            host.append((v, hin, hout))
+            hout = [[torch.empty(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
+                    for _ in range(depth)]
+            host.append((v, hin, hout, torch.cuda.Stream()))   # own compute stream: no head-of-line blocking
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
         t0 = time.perf_counter()
-        # software pipeline over the two sequences: each has one step in flight; the upload of a sequence's
-        # next step overlaps the other sequence's download (full-duplex PCIe).  Every step's outputs are
-        # waited for on the host (wait_host) before that sequence is issued again.
-        for v, hin, hout in host:
-            v.apply_host(hin, hout, wait=False)
+        # software pipeline: every sequence keeps `depth` steps in flight.  The upload of step n+1 starts when
+        # the kernels of step n have consumed the device inputs and overlaps the download of step n
+        # (full-duplex PCIe); every step's outputs are waited for on the host (wait_host) before its host
+        # buffers are handed to a later step.
+        for n in range(min(depth, e2e_steps)):
+            for v, hin, hout, stream in host:
+                v.apply_host(hin, hout[n % depth], stream=stream, wait=False)
         for n in range(e2e_steps):
-            for v, hin, hout in host:
-                v.wait_host()                        # this step's outputs of the sequence are on the host
-                if n + 1 < e2e_steps:
-                    v.apply_host(hin, hout, wait=False)
+            for v, hin, hout, stream in host:
+                v.wait_host()                        # step n's outputs of the sequence are on the host
+                if n + depth < e2e_steps:
+                    v.apply_host(hin, hout[n % depth], stream=stream, wait=False)
         torch.cuda.synchronize()
         e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
         if world > 1:
             t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_ms = float(t.item())
-        h2d = sum(sum(1 for t in hin if t is not None) for _, hin, _ in host) * host[0][0].field_bytes
-        d2h = sum(len(hout) for _, _, hout in host) * host[0][0].field_bytes
+        h2d = sum(sum(1 for t in hin if t is not None) for _, hin, _, _ in host) * host[0][0].field_bytes
+        d2h = sum(len(hout[0]) for _, _, hout, _ in host) * host[0][0].field_bytes
         e2e = {"value": round(2 * points * world / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpoints/s",
                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 2),
-               "steps": e2e_steps, "constants_resident": constants, "api": "Variant.apply_host(wait=False) + wait_host per sequence and step (absinthe_variant_apply_host_async), one step of each sequence in flight"}
+               "steps": e2e_steps, "constants_resident": constants, "steps_in_flight": depth,
+               "api": "Variant.apply_host(wait=False) + wait_host per sequence and step "
+                      "(absinthe_variant_apply_host_async / absinthe_variant_wait_host)"}
 
     if rank == 0:
         line = {
             "metric": "fused_sequence_throughput", "value": round(value, 1), "unit": "Mpoints/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": round(ms_per_step, 4),
+            "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "breakdown": breakdown,

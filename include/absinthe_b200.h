@@ -108,8 +108,12 @@ int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inpu
                                 double* const* h_outputs, void* stream);
 
 /* The same without the final synchronisation: H2D on a private copy stream, the sequence on `stream`,
- * D2H on a second copy stream, so the copies of several variants overlap (full-duplex PCIe).
- * absinthe_variant_wait_host blocks until the outputs of the last async call are in host memory. */
+ * D2H on a second copy stream, so uploads and downloads overlap (full-duplex PCIe).  Up to TWO steps of
+ * a variant may be in flight: the upload of step n+1 starts as soon as the kernels of step n have read
+ * the device inputs, its kernels start once the download of step n has read the device outputs -- the
+ * caller hands step n+1 its own host output buffers.  absinthe_variant_wait_host blocks until the
+ * outputs of the OLDEST step not yet waited for are in host memory (no-op when none is pending); a
+ * third async call without a wait in between fails with -6. */
 int absinthe_variant_apply_host_async(absinthe_variant* v, const double* const* h_inputs,
                                       double* const* h_outputs, void* stream);
 int absinthe_variant_wait_host(absinthe_variant* v);

@@ -135,3 +135,38 @@ def test_host_path_matches_device_path(launcher_lib):
     for name, t in zip(v.outputs, host_out):
         assert torch.equal(t, want[name].cpu()), name
     v.close()
+
+
+def test_two_host_steps_in_flight(launcher_lib):
+    """The async host path keeps two steps in flight; each step's outputs match the synchronous call's."""
+    from absinthe_b200.launcher import LauncherError
+    program = P.make_program("diffusion", None, [(2, 8, 4)], domain=(96, 64, 20))
+    v = Variant.from_program(P.clone(program))
+    v.bind([v.empty_field() for _ in v.inputs], [v.empty_field() for _ in v.outputs])
+    steps = []
+    for seed in (1, 2, 3, 4):
+        inputs, _ = make_inputs(program, seed=seed)
+        host_in = [inputs[n].cpu().pin_memory() for n in v.inputs]
+        want = [torch.empty(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
+        v.apply_host(host_in, want)
+        steps.append((host_in, want))
+    outs = [[torch.zeros(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs] for _ in range(2)]
+    v.apply_host(steps[0][0], outs[0], wait=False)
+    v.apply_host(steps[1][0], outs[1], wait=False)
+    with pytest.raises(LauncherError):
+        v.apply_host(steps[2][0], outs[0], wait=False)       # a third step needs a wait first
+    for n in range(4):
+        v.wait_host()
+        for name, got, want in zip(v.outputs, outs[n % 2], steps[n][1]):
+            assert torch.equal(got, want), (n, name)
+        if n + 2 < 4:
+            v.apply_host(steps[n + 2][0], outs[n % 2], wait=False)
+    v.wait_host()                                            # nothing pending: returns at once
+    # a synchronous call drains steps still in flight before it touches the device fields
+    v.apply_host(steps[0][0], outs[0], wait=False)
+    v.apply_host(steps[1][0], outs[1])
+    for got, want in zip(outs[0], steps[0][1]):
+        assert torch.equal(got, want)
+    for got, want in zip(outs[1], steps[1][1]):
+        assert torch.equal(got, want)
+    v.close()
