@@ -11,6 +11,8 @@ fixtures it writes are small and committed, so the tests that use them run anywh
                                  (srand(0)/rand(), periodic) and of the outputs its own
                                  ``compute_reference`` computes from them, strict IEEE build
 * ``parse_results.json``         rows the reference's ``parse_results`` extracts from a sample log
+* ``shipped_medians.json``       estimate and median measurement of every variant the reference ships
+                                 results for (``*/estimates.csv`` joined with ``*/results.csv``)
 """
 
 import hashlib
@@ -168,10 +170,27 @@ def shipped_variants():
     return out
 
 
+def shipped_medians():
+    """VAR -> [EST, median(TOTAL - HALO)] of the reference's shipped estimates.csv / results.csv."""
+    import csv
+    import statistics
+    out = {}
+    for kernel in ("diffusion", "advection", "fastwaves"):
+        with open(os.path.join(REFERENCE, kernel, "estimates.csv")) as handle:
+            est = {r["VAR"]: float(r["EST"]) for r in csv.DictReader(handle)}
+        mea = {}
+        with open(os.path.join(REFERENCE, kernel, "results.csv")) as handle:
+            for r in csv.DictReader(handle):
+                mea.setdefault(r["VAR"], []).append(float(r["TOTAL"]) - float(r["HALO"]))
+        out[kernel] = {var: [est[var], statistics.median(v)] for var, v in sorted(mea.items()) if var in est}
+    return out
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     for name, fn in (("stencil_fingerprints", stencil_fingerprints), ("analysis", analysis_fixtures),
                      ("parse_results", parse_fixture), ("shipped_variants", shipped_variants),
+                     ("shipped_medians", shipped_medians),
                      ("reference_digests", reference_digests)):
         with open(os.path.join(GOLDEN, name + ".json"), "w") as handle:
             json.dump(fn(), handle, indent=1, sort_keys=True)
