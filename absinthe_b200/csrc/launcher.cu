@@ -299,6 +299,29 @@ struct Group {
     double* scratch = nullptr;
 };
 
+// interior comparison of the reference's verifier (ref template_tiling.cpp:383-392): a point is an error
+// when |expected - actual| > max(|expected|, |actual|) * tolerance (so NaN never counts as one)
+__global__ void compare_kernel(const double* __restrict__ expected, const double* __restrict__ actual,
+                               Geometry g, double tolerance, unsigned long long* counters) {
+    const long cells = (long)g.X * g.Y * g.Z;
+    unsigned long long errors = 0, matches = 0;
+    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < cells; n += (long)gridDim.x * blockDim.x) {
+        const long i = n % g.X, j = (n / g.X) % g.Y, k = n / ((long)g.X * g.Y);
+        const long at = (i + g.HX) + (j + g.HY) * g.row() + (k + g.HZ) * g.plane();
+        const double e = expected[at], a = actual[at];
+        if (fabs(e - a) > fmax(fabs(e), fabs(a)) * tolerance) ++errors;
+        else ++matches;
+    }
+    for (int d = 16; d > 0; d >>= 1) {
+        errors += __shfl_down_sync(0xffffffffu, errors, d);
+        matches += __shfl_down_sync(0xffffffffu, matches, d);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (errors) atomicAdd(&counters[0], errors);
+        if (matches) atomicAdd(&counters[1], matches);
+    }
+}
+
 }  // namespace
 
 struct absinthe_variant {
@@ -898,6 +921,29 @@ int absinthe_halo_unpack(double* d_field, const double* d_buffer, int X, int Y, 
     long total = g.planes() * width * g.row();
     pack_kernel<<<launch_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(d_field, const_cast<double*>(d_buffer), g, j0, width, 1);
     RT(cudaGetLastError());
+    return 0;
+}
+
+int absinthe_compare_fields(const double* d_expected, const double* d_actual, int X, int Y, int Z, int HX,
+                            int HY, int HZ, double tolerance, unsigned long long* errors,
+                            unsigned long long* matches, void* stream) {
+    if (!d_expected || !d_actual || !errors || !matches) return fail(-3, "absinthe_compare_fields: null argument");
+    Geometry g{X, Y, Z, HX, HY, HZ};
+    unsigned long long* counters = nullptr;
+    RT(cudaMalloc(&counters, 2 * sizeof(unsigned long long)));
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), s);
+    if (e == cudaSuccess) {
+        compare_kernel<<<launch_grid((long)X * Y * Z, 256), 256, 0, s>>>(d_expected, d_actual, g, tolerance, counters);
+        e = cudaGetLastError();
+    }
+    unsigned long long host[2] = {0, 0};
+    if (e == cudaSuccess) e = cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    cudaFree(counters);
+    if (e != cudaSuccess) return fail((int)e, "absinthe_compare_fields: %s", cudaGetErrorString(e));
+    *errors = host[0];
+    *matches = host[1];
     return 0;
 }
 

@@ -649,7 +649,7 @@ class Plan:
         training = p.get("TRAINING", {})
         lines = ["absinthe-variant 1", "name %s" % (p.get("VARIANT") or p.get("NAME") or "variant"),
                  "# runs %d" % p.get("RUNS", 64), "# flush %d" % int(bool(p.get("FLUSH", True))),
-                 "# training %d" % int(bool(training)),
+                 "# training %d" % int(bool(training))] + (["# verify 1"] if p.get("VERIFY") else []) + [
                  "domain %d %d %d %d %d %d" % tuple(p[k] for k in ("X", "Y", "Z", "HX", "HY", "HZ"))]
         for name in self.inputs:
             lines.append("field %s in" % name)

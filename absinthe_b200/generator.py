@@ -17,12 +17,15 @@ reference -- ``generate_code(template, name, program)`` (ref :41-59),
 
 import csv
 import hashlib
+import math
 import os
 import subprocess
 import sys
 from collections import deque
 
 from jinja2 import Environment, FileSystemLoader
+
+from copy import deepcopy
 
 from . import analysis as A
 from .emitter import Plan
@@ -82,10 +85,45 @@ def render(template, program):
     return source, plan.descriptor_text(), plan.nvcc_flags()
 
 
+REFERENCE_SUFFIX = "_reference"
+REFERENCE_TILE = (128, 8, 4)      # points per tile of the sequential reference variant
+
+
+def sequential_reference(program):
+    """The program of ``compute_reference`` (ref template_tiling.cpp:162-177) as a variant of its own.
+
+    Every stencil becomes a group, in the order the reference walks them (groups in TILING order,
+    stencils in group order); the launcher applies the periodic update to every group output, i.e.
+    after each stencil, and intermediates live in global memory -- the sequential algorithm on the
+    GPU.  A ``VERIFY`` program is checked against it at run time (ref :276-282, :378-396).
+    """
+    order = []
+    for outer in program["TILING"]["GROUPS"]:
+        for inner in outer.get("GROUPS", []):
+            order += [s["NAME"] if isinstance(s, dict) else s for s in inner["STENCILS"]]
+    ref = {k: deepcopy(v) for k, v in program.items() if k not in ("TILING", "SCHEDULE", "CUDA")}
+    ref["SEQUENCE"] = list(order)
+    ref["VARIANT"] = "%s%s" % (program.get("VARIANT") or program.get("NAME") or "variant", REFERENCE_SUFFIX)
+    ref["VERIFY"] = False
+    counts = tuple(max(1, math.ceil(program[d] / t)) for d, t in zip("XYZ", REFERENCE_TILE))
+    tiling = program["TILING"]
+    ref["TILING"] = {
+        "NX": tiling.get("NX", 1), "NY": tiling.get("NY", 1), "NZ": tiling.get("NZ", 1),
+        "GROUPS": [{"GROUPS": [{"STENCILS": [name], "NX": counts[0], "NY": counts[1], "NZ": counts[2]}]}
+                   for name in order]}
+    return ref
+
+
 def generate_code(template, name, program):
-    """Render ``program`` to ``name`` (a .cu path) and write ``<stem>.desc`` beside it."""
-    source, descriptor, flags = render(template, program)
+    """Render ``program`` to ``name`` (a .cu path) and write ``<stem>.desc`` beside it.
+
+    A program with ``VERIFY`` set also gets ``<stem>_reference.cu/.desc`` (``sequential_reference``),
+    which the runner executes once and compares the outputs with (ref template_tiling.cpp:378-396).
+    """
     stem = name[:-3] if name.endswith(".cu") else name
+    if program.get("VERIFY") and template == "template_tiling.cu" and not stem.endswith(REFERENCE_SUFFIX):
+        generate_code(template, stem + REFERENCE_SUFFIX + ".cu", sequential_reference(program))
+    source, descriptor, flags = render(template, program)
     with open(stem + ".cu", "w") as handle:
         handle.write(source)
     with open(stem + ".desc", "w") as handle:
@@ -106,8 +144,11 @@ def generate_makefile(name, experiments):
     with open(name, "w", newline="\n") as handle:
         handle.write("\nNVCC=nvcc\n")
         handle.write("NVCCFLAGS= \\\n\t" + " \\\n\t".join(flags) + "\n\n")
-        handle.write("all: " + " ".join(key + ".cubin" for key in experiments) + "\n\n")
-        for key in experiments:
+        # a VERIFY experiment comes with its sequential reference variant (generate_code)
+        keys = [key + tail for key, e in experiments.items()
+                for tail in ([""] + ([REFERENCE_SUFFIX] if e.get("VERIFY") and not e.get("TRAINING") else []))]
+        handle.write("all: " + " ".join(key + ".cubin" for key in keys) + "\n\n")
+        for key in keys:
             handle.write("%s.cubin: %s.cu\n" % (key, key))
             handle.write("\t$(NVCC) $(NVCCFLAGS) -cubin -o $@ $<\n\n")
         handle.write("clean:\n\trm -f *.cubin\n")

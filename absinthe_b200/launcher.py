@@ -27,7 +27,7 @@ SYMBOLS = [
     "absinthe_variant_apply_host", "absinthe_make_periodic", "absinthe_fill_rand", "absinthe_flush_l2",
     "absinthe_halo_pack", "absinthe_halo_unpack", "absinthe_make_periodic_ik",
     "absinthe_variant_pack_group", "absinthe_variant_unpack_group",
-    "absinthe_variant_apply_host_async", "absinthe_variant_wait_host",
+    "absinthe_variant_apply_host_async", "absinthe_variant_wait_host", "absinthe_compare_fields",
 ]
 
 
@@ -75,6 +75,8 @@ def load_library(path=None):
                                                 c.c_void_p]
     lib.absinthe_variant_apply_host_async.argtypes = lib.absinthe_variant_apply_host.argtypes
     lib.absinthe_variant_wait_host.argtypes = [c.c_void_p]
+    lib.absinthe_compare_fields.argtypes = [c.c_void_p, c.c_void_p] + [c.c_int] * 6 + [
+        c.c_double, c.POINTER(c.c_ulonglong), c.POINTER(c.c_ulonglong), c.c_void_p]
     lib.absinthe_make_periodic.argtypes = [c.c_void_p] + [c.c_int] * 6 + [c.c_void_p]
     lib.absinthe_make_periodic_ik.argtypes = [c.c_void_p] + [c.c_int] * 6 + [c.c_void_p]
     lib.absinthe_fill_rand.argtypes = [c.c_void_p, c.c_size_t, c.c_uint, c.c_int]
@@ -236,6 +238,16 @@ def make_periodic(tensor, dims, stream=None, ik_only=False):
     lib = load_library()
     fn = lib.absinthe_make_periodic_ik if ik_only else lib.absinthe_make_periodic
     check(lib, fn(tensor.data_ptr(), *dims, _stream_handle(stream)), "absinthe_make_periodic")
+
+
+def compare_fields(expected, actual, dims, tolerance=1e-7, stream=None):
+    """(errors, matches) over the interior with the reference's relative test (ref template_tiling.cpp:383-392)."""
+    lib = load_library()
+    errors, matches = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
+    check(lib, lib.absinthe_compare_fields(expected.data_ptr(), actual.data_ptr(), *dims, tolerance,
+                                           ctypes.byref(errors), ctypes.byref(matches), _stream_handle(stream)),
+          "absinthe_compare_fields")
+    return errors.value, matches.value
 
 
 def flush_l2(stream=None):

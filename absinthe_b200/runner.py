@@ -38,25 +38,54 @@ def prepare_inputs(variant, seed=0, on_device=False):
     return tensors
 
 
-def run_variant(stem, runs, flush=True, training=False, device=0, out=sys.stdout):
-    import torch
+def compute_reference(stem, inputs, device=0):
+    """Outputs of the sequential reference variant ``<stem>_reference`` (generator.sequential_reference:
+    every stencil over the whole domain, periodic update after each -- ref template_tiling.cpp:162-177)."""
+    from .generator import REFERENCE_SUFFIX
     from .launcher import Variant
+    reference = Variant(stem + REFERENCE_SUFFIX + ".desc", stem + REFERENCE_SUFFIX + ".cubin", device)
+    expected = [reference.empty_field() for _ in reference.outputs]
+    reference.bind(inputs, expected)
+    reference.apply()
+    names = list(reference.outputs)
+    reference.close()
+    return dict(zip(names, expected))
+
+
+def run_variant(stem, runs, flush=True, training=False, device=0, out=sys.stdout, verify=False):
+    import torch
+    from .launcher import Variant, compare_fields
     variant = Variant(stem + ".desc", stem + ".cubin", device)
     name = open(stem + ".desc").read().split("\n")[1].split(" ", 1)[1]
     print("-> configuration", file=out)
     print("   - variant " + name, file=out)
     print("   - domain %d, %d, %d" % (variant.X, variant.Y, variant.Z), file=out)
     print("   - runs %d" % runs, file=out)
+    print("   - verify %s" % bool(verify), file=out)
     print("   - device " + torch.cuda.get_device_name(device), file=out)
     inputs = prepare_inputs(variant, on_device=training)
     outputs = [variant.empty_field() for _ in variant.outputs]
+    expected = None
+    if verify:
+        print("-> computing reference...", file=out)
+        expected = compute_reference(stem, dict(zip(variant.inputs, inputs)), device)
     variant.bind(inputs, outputs)
     total, halo = variant.run(runs, flush=flush, training=training)
-    variant.close()
     for t, h in zip(total, halo):
         print("-> apply stencils...", file=out)
         print("   - total time (min/median/max) [ms]: %g" % t, file=out)
         print("   - halo time (min/median/max) [ms]: %g" % h, file=out)
+    if verify:
+        # ref template_tiling.cpp:378-396: interior of every output, relative 1e-7
+        print("-> verifying...", file=out)
+        dims = (variant.X, variant.Y, variant.Z, variant.HX, variant.HY, variant.HZ)
+        errors = matches = 0
+        for field, got in zip(variant.outputs, outputs):
+            e, m = compare_fields(expected[field], got, dims)
+            errors, matches = errors + e, matches + m
+        print("   - %d errors" % errors, file=out)
+        print("   - %d matches" % matches, file=out)
+    variant.close()
     return np.array(total), np.array(halo)
 
 
@@ -77,7 +106,8 @@ def main(argv=None):
         runs = args.runs or int(meta.get("runs", 64))
         flush = not args.no_flush and meta.get("flush", "1") == "1"
         training = meta.get("training", "0") == "1"
-        run_variant(stem, runs, flush=flush, training=training, device=args.device)
+        run_variant(stem, runs, flush=flush, training=training, device=args.device,
+                    verify=meta.get("verify", "0") == "1")
         sys.stdout.flush()
 
 

@@ -128,6 +128,13 @@ void absinthe_fill_rand(double* h_dst, size_t count, unsigned seed, int reseed);
 /* write a buffer larger than L2 so the next kernel starts cold */
 int absinthe_flush_l2(void* stream);
 
+/* the reference's verifier (ref template_tiling.cpp:378-396) on device fields: over the interior, a point
+ * counts as an error when |expected - actual| > max(|expected|, |actual|) * tolerance (the reference
+ * uses 1e-7), else as a match.  Synchronises `stream`. */
+int absinthe_compare_fields(const double* d_expected, const double* d_actual, int X, int Y, int Z,
+                            int HX, int HY, int HZ, double tolerance, unsigned long long* errors,
+                            unsigned long long* matches, void* stream);
+
 /* ---- multi-GPU halo faces (domain decomposed along j; rows are contiguous per k-plane) ---- */
 
 /* pack `width` rows starting at padded row `j0` of every k-plane into a dense buffer

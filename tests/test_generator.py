@@ -100,3 +100,34 @@ def test_branchify_only_touches_expensive_conditionals():
     assert out.rstrip().endswith("auto res = uteu(i,j,k) + ( sel_0 );")
     top = branchify(adv["uteu"])
     assert top.count("if (uatu(i,j,k) > 0.0)") == 1 and "auto res = sel_0 ;" in top
+
+
+def test_verify_emits_the_sequential_reference_variant(tmp_path):
+    """VERIFY programs come with <name>_reference: one group per stencil, in compute_reference's order."""
+    sequence = P.KERNELS["fastwaves"][1]()
+    program = P.make_program("fastwaves", [sequence[:6], sequence[6:]], [(2, 4, 6), (1, 2, 3)],
+                             variant="fastwaves-split", VERIFY=True)
+    ref = G.sequential_reference(program)
+    assert [g["GROUPS"][0]["STENCILS"] for g in ref["TILING"]["GROUPS"]] == [[name] for name in sequence]
+    assert all((g["GROUPS"][0]["NX"], g["GROUPS"][0]["NY"], g["GROUPS"][0]["NZ"]) == (1, 8, 15)
+               for g in ref["TILING"]["GROUPS"])
+    assert ref["OUTPUTS"] == program["OUTPUTS"] and ref["VERIFY"] is False and "CUDA" not in ref
+    assert ref["VARIANT"] == "fastwaves-split_reference"
+
+    G.generate_code("template_tiling.cu", str(tmp_path / "fw.cu"), program)
+    assert sorted(os.listdir(tmp_path)) == ["fw.cu", "fw.desc", "fw_reference.cu", "fw_reference.desc"]
+    assert "# verify 1" in (tmp_path / "fw.desc").read_text().split("\n")
+    desc = (tmp_path / "fw_reference.desc").read_text()
+    assert "# verify" not in desc
+    assert desc.count("\ngroup ") == len(sequence)
+    # the same program analysed twice (a driver may pass an analysed dict) gives the same reference
+    assert G.sequential_reference(program)["SEQUENCE"] == sequence
+    # intermediates live in global memory and get the periodic update after their stencil
+    for name in ("ppgk", "ppgc", "ppgu", "ppgv", "udc", "vdc"):
+        assert "field %s tmp" % name in desc and "halo %s" % name in desc
+
+    plain = P.make_program("advection", variant="plain")
+    G.generate_makefile(str(tmp_path / "Makefile"), {"fw": program, "plain": plain})
+    makefile = (tmp_path / "Makefile").read_text()
+    assert "all: fw.cubin fw_reference.cubin plain.cubin\n" in makefile
+    assert "fw_reference.cubin: fw_reference.cu\n" in makefile and "plain_reference" not in makefile

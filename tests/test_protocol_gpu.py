@@ -55,3 +55,38 @@ def test_unbound_variant_is_an_error(launcher_lib):
     with pytest.raises(LauncherError, match="no buffers bound"):
         v.apply()
     v.close()
+
+
+@pytest.mark.parametrize("kernel,outputs", [("diffusion", 4), ("advection", 2), ("fastwaves", 3)])
+def test_verify_runs_the_sequential_reference(launcher_lib, tmp_path, kernel, outputs):
+    """VERIFY: the variant is compared with the per-stencil sequential variant (ref template_tiling.cpp:378-396)."""
+    from absinthe_b200.runner import run_variant
+    import subprocess
+    program = P.make_program(kernel, [seq(kernel)], [(2, 4, 6)], variant=kernel + "-fused", RUNS=2, VERIFY=True)
+    program["CUDA"] = {"INLINE": "all", "BLOCK": (2, 1), "SHUFFLE": True, "FUSE_HALO": True}
+    stem = str(tmp_path / kernel)
+    G.generate_code("template_tiling.cu", stem + ".cu", program)
+    for s in (stem, stem + G.REFERENCE_SUFFIX):
+        subprocess.check_call(G.nvcc_command(program["CUDA"]["NVCC_FLAGS"], s + ".cu", s + ".cubin"))
+    out = io.StringIO()
+    run_variant(stem, 2, out=out, verify=True)
+    lines = out.getvalue().splitlines()
+    assert "   - verify True" in lines and "-> computing reference..." in lines
+    assert lines[-3:] == ["-> verifying...", "   - 0 errors", "   - %d matches" % (outputs * 64 * 64 * 60)]
+
+
+def test_compare_fields_counts_like_the_reference(launcher_lib):
+    import torch
+    from absinthe_b200.launcher import compare_fields
+    dims = (20, 6, 5, 3, 3, 3)
+    shape = (5 + 6, 6 + 6, 20 + 6)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    a = torch.rand(shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+    b = a.clone()
+    assert compare_fields(a, b, dims) == (0, 20 * 6 * 5)
+    b[3 + 2, 3 + 1, 3 + 7] *= 1.0 + 3e-7          # beyond the 1e-7 relative tolerance
+    b[3 + 0, 3 + 0, 3 + 0] *= 1.0 + 5e-8          # within it
+    b[0, 0, 0] = 99.0                             # halo: not looked at
+    b[3 + 4, 3 + 5, 3 + 19] = float("nan")        # NaN never compares greater: a match, as in the reference
+    assert compare_fields(a, b, dims) == (1, 20 * 6 * 5 - 1)
+    assert compare_fields(a, b, dims, tolerance=1e-8) == (2, 20 * 6 * 5 - 2)
