@@ -22,10 +22,12 @@ def main(path, out=None):
         for i, h in enumerate(hdr):
             if h in keys:
                 d[h] = vals[i] + (" " + units[i] if units[i] else "")
-            elif "warp_issue_stalled" in h and h.endswith("per_warp_active.pct"):
+            elif h.startswith("smsp__average_warps_issue_stalled_") and h.endswith("_per_issue_active.ratio"):
+                # warps stalled for this reason per issued instruction (the "Warp State" chart of the ncu UI)
                 try:
-                    if float(vals[i]) >= 3.0:
-                        d.setdefault("stalls_pct", {})[h.replace("smsp__warp_issue_stalled_", "").replace("_per_warp_active.pct", "")] = float(vals[i])
+                    if float(vals[i]) >= 0.1:
+                        name = h[len("smsp__average_warps_issue_stalled_"):-len("_per_issue_active.ratio")]
+                        d.setdefault("stalled_warps_per_issue", {})[name] = round(float(vals[i]), 3)
                 except ValueError:
                     pass
         result.append(d)
