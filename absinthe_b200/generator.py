@@ -220,16 +220,18 @@ def build_variant(program, template="template_tiling.cu", cache_dir=None):
     stem = os.path.join(cache_dir, tag)
     if not (os.path.exists(stem + ".cubin") and os.path.exists(stem + ".desc")):
         # several ranks may build the same variant at once: everything goes through per-process
-        # temporaries and is published with atomic renames
+        # temporaries and is published with atomic renames.  The source is published first and compiled
+        # under its final name (the tag is its content hash, so concurrent writers agree byte for byte):
+        # -lineinfo then points at a file that exists, which `ncu --import-source on` needs.
         mine = "%s.%d" % (stem, os.getpid())
         with open(mine + ".cu", "w") as handle:
             handle.write(source)
-        proc = subprocess.run(nvcc_command(flags, mine + ".cu", mine + ".tmp"), capture_output=True, text=True)
+        os.replace(mine + ".cu", stem + ".cu")
+        proc = subprocess.run(nvcc_command(flags, stem + ".cu", mine + ".tmp"), capture_output=True, text=True)
         if proc.returncode != 0:
-            raise RuntimeError("nvcc failed for %s:\n%s" % (mine + ".cu", proc.stderr[-4000:]))
+            raise RuntimeError("nvcc failed for %s:\n%s" % (stem + ".cu", proc.stderr[-4000:]))
         with open(mine + ".desc.tmp", "w") as handle:
             handle.write(descriptor)
-        os.replace(mine + ".cu", stem + ".cu")
         os.replace(mine + ".tmp", stem + ".cubin")
         os.replace(mine + ".desc.tmp", stem + ".desc")
     return stem + ".desc", stem + ".cubin"
