@@ -379,56 +379,54 @@ def run_gpu_arm(args):
                 "frac_of_8TBps": round(dominant[2] / 8000.0, 4)}
 
     # end to end through the public API with HOST buffers (pinned), copies inside the timed region
-    e2e = None
     launches = sum(item["v"].launches for item in variants) * args.steps
-    if True:
-        e2e_steps = max(1, min(args.steps, 10))
-        host = []
-        constants = {}
-        nfields = sum(len(item["v"].inputs) + 2 * len(item["v"].outputs) for item in variants)
-        local = int(os.environ.get("LOCAL_WORLD_SIZE", world))
-        # two steps of a sequence in flight need their own host output buffers; fall back to one step in
-        # flight when the box could not pin that much memory for all its ranks
-        depth = 2 if _available_host_bytes() > 2 * local * nfields * variants[0]["v"].field_bytes else 1
-        for (name, program), item in zip(workload_programs(), variants):
-            v = item["v"]
-            # the program's CONSTANTS (mask; wgtfac, hhl, rho, dzdx, dzdy) stay resident on the device as
-            # bound; every step uploads the fields that change from step to step and downloads all outputs
-            const = [n for n in v.inputs if n in program.get("CONSTANTS", [])]
-            constants[name] = const
-            hin = [None if n in const else t.cpu().pin_memory() for n, t in zip(v.inputs, item["ins"])]
-            hout = [[torch.empty(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
-                    for _ in range(depth)]
-            host.append((v, hin, hout, torch.cuda.Stream()))   # own compute stream: no head-of-line blocking
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        t0 = time.perf_counter()
-        # software pipeline: every sequence keeps `depth` steps in flight.  The upload of step n+1 starts when
-        # the kernels of step n have consumed the device inputs and overlaps the download of step n
-        # (full-duplex PCIe); every step's outputs are waited for on the host (wait_host) before its host
-        # buffers are handed to a later step.
-        for n in range(min(depth, e2e_steps)):
-            for v, hin, hout, stream in host:
+    e2e_steps = max(1, min(args.steps, 10))
+    host = []
+    constants = {}
+    nfields = sum(len(item["v"].inputs) + 2 * len(item["v"].outputs) for item in variants)
+    ranks_on_box = int(os.environ.get("LOCAL_WORLD_SIZE", world))
+    # two steps of a sequence in flight need their own host output buffers; fall back to one step in
+    # flight when the box could not pin that much memory for all its ranks
+    depth = 2 if _available_host_bytes() > 2 * ranks_on_box * nfields * variants[0]["v"].field_bytes else 1
+    for (name, program), item in zip(workload_programs(), variants):
+        v = item["v"]
+        # the program's CONSTANTS (mask; wgtfac, hhl, rho, dzdx, dzdy) stay resident on the device as
+        # bound; every step uploads the fields that change from step to step and downloads all outputs
+        const = [n for n in v.inputs if n in program.get("CONSTANTS", [])]
+        constants[name] = const
+        hin = [None if n in const else t.cpu().pin_memory() for n, t in zip(v.inputs, item["ins"])]
+        hout = [[torch.empty(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
+                for _ in range(depth)]
+        host.append((v, hin, hout, torch.cuda.Stream()))   # own compute stream: no head-of-line blocking
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    # software pipeline: every sequence keeps `depth` steps in flight.  The upload of step n+1 starts when
+    # the kernels of step n have consumed the device inputs and overlaps the download of step n
+    # (full-duplex PCIe); every step's outputs are waited for on the host (wait_host) before its host
+    # buffers are handed to a later step.
+    for n in range(min(depth, e2e_steps)):
+        for v, hin, hout, stream in host:
+            v.apply_host(hin, hout[n % depth], stream=stream, wait=False)
+    for n in range(e2e_steps):
+        for v, hin, hout, stream in host:
+            v.wait_host()                        # step n's outputs of the sequence are on the host
+            if n + depth < e2e_steps:
                 v.apply_host(hin, hout[n % depth], stream=stream, wait=False)
-        for n in range(e2e_steps):
-            for v, hin, hout, stream in host:
-                v.wait_host()                        # step n's outputs of the sequence are on the host
-                if n + depth < e2e_steps:
-                    v.apply_host(hin, hout[n % depth], stream=stream, wait=False)
-        torch.cuda.synchronize()
-        e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
-        if world > 1:
-            t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_ms = float(t.item())
-        h2d = sum(sum(1 for t in hin if t is not None) for _, hin, _, _ in host) * host[0][0].field_bytes
-        d2h = sum(len(hout[0]) for _, _, hout, _ in host) * host[0][0].field_bytes
-        e2e = {"value": round(2 * points * world / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpoints/s",
-               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 2),
-               "steps": e2e_steps, "constants_resident": constants, "steps_in_flight": depth,
-               "api": "Variant.apply_host(wait=False) + wait_host per sequence and step "
-                      "(absinthe_variant_apply_host_async / absinthe_variant_wait_host)"}
+    torch.cuda.synchronize()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    h2d = sum(sum(1 for t in hin if t is not None) for _, hin, _, _ in host) * host[0][0].field_bytes
+    d2h = sum(len(hout[0]) for _, _, hout, _ in host) * host[0][0].field_bytes
+    e2e = {"value": round(2 * points * world / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpoints/s",
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 2),
+           "steps": e2e_steps, "constants_resident": constants, "steps_in_flight": depth,
+           "api": "Variant.apply_host(wait=False) + wait_host per sequence and step "
+                  "(absinthe_variant_apply_host_async / absinthe_variant_wait_host)"}
 
     if rank == 0:
         line = {
