@@ -174,14 +174,14 @@ def cpu_baseline(steps=3, warmup=1):
     """Mpoints/s of the CPU arm on the bounded slab; prefers the real reference build."""
     from absinthe_b200 import programs as P
     points = CPU_SLAB[0] * CPU_SLAB[1] * CPU_SLAB[2]
-    total_ms, kind, threads, detail = 0.0, "reference", 1, {}
+    total_ms, kind, threads, detail, timed = 0.0, "reference", 1, {}, steps
     for name, program in workload_programs():
         got = cpu_reference_time(name, steps, warmup)
         if got is None:
             kind = "port"
             break
         total_ms += got[0]
-        threads = got[2]
+        timed, threads = got[1], got[2]      # the binary holds RUNS = 6: at most 6 - warmup timed runs
         detail[name] = got[0]
     if kind == "port":
         total_ms, threads, detail = 0.0, 1, {}
@@ -194,7 +194,7 @@ def cpu_baseline(steps=3, warmup=1):
         sample = "sequential oracle port, %dx%dx%d slab, one pass per sequence" % small
     else:
         sample = ("reference OpenMP build (g++ -O3 -ffast-math -fopenmp) of the same variants on a "
-                  "%dx%dx%d slab, median of %d timed runs per sequence" % (CPU_SLAB + (steps,)))
+                  "%dx%dx%d slab, median of %d timed runs per sequence" % (CPU_SLAB + (timed,)))
     value = 2 * points / (total_ms * 1e-3) / 1e6
     return {"value": value, "unit": "Mpoints/s", "cores": threads, "kind": kind, "sample": sample,
             "ms_per_sequence": detail}
