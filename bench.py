@@ -215,7 +215,7 @@ def run_reference_arm(args):
         "e2e": {"value": base["value"], "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
 
 
 def _available_host_bytes():
@@ -249,8 +249,6 @@ def run_gpu_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        # keep NCCL's version banner off stdout (rank 0 prints exactly one JSON line)
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/absinthe_nccl.%h.%p.log")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
     sampler = ClockSampler(local)                  # started early: nvidia-smi takes a while to come up
@@ -442,10 +440,27 @@ def run_gpu_arm(args):
                 line["cpu_baseline"] = cpu_baseline()
             except Exception as exc:
                 line["cpu_baseline"] = {"error": str(exc)[:200]}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+RESULT = sys.stdout
+
+
+def claim_stdout():
+    """Keep stdout for the one JSON line: whatever libraries write to file descriptor 1 (NCCL prints a
+    version banner there under torchrun, whatever NCCL_DEBUG_FILE says) is sent to stderr instead."""
+    global RESULT
+    sys.stdout.flush()
+    RESULT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def emit(line):
+    RESULT.write(json.dumps(line) + "\n")
+    RESULT.flush()
 
 
 def main():
@@ -456,6 +471,7 @@ def main():
     parser.add_argument("--impl", default="absinthe_b200", choices=["absinthe_b200", "reference"])
     parser.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = parser.parse_args()
+    claim_stdout()
     if args.impl == "reference":
         run_reference_arm(args)
     else:
