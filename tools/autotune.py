@@ -26,9 +26,11 @@ def make(kernel, assignment, shape, domain, cuda):
     from absinthe_b200.analysis import ceil_div
     seq = P.KERNELS[kernel][1]()
     groups = P.split_sequence(seq, assignment)
-    counts = tuple(max(1, ceil_div(d, s)) for d, s in zip(domain, shape))
-    program = P.make_program(kernel, groups, [counts] * len(groups), domain=domain,
-                             variant="%s-%s" % (kernel, "x".join(map(str, shape))))
+    # one tile shape (points) for every group, or a list of shapes, one per group
+    shapes = [shape] * len(groups) if isinstance(shape[0], int) else list(shape)
+    counts = [tuple(max(1, ceil_div(d, s)) for d, s in zip(domain, sh)) for sh in shapes]
+    program = P.make_program(kernel, groups, counts, domain=domain,
+                             variant="%s-%s" % (kernel, "_".join("x".join(map(str, sh)) for sh in shapes)))
     program["CUDA"] = dict(cuda)
     return program
 
@@ -73,11 +75,14 @@ def main():
         cfg = json.load(open(os.path.join(ROOT, "absinthe_b200", "tuned.json")))[args.kernel]
         args.assignment = "".join(str(a) for a in cfg["assignment"])
         args.tiles = "x".join(str(ceil_div(d, n)) for d, n in zip(domain, cfg["tiles"][0]))
+        tuned_shapes = [tuple(ceil_div(d, n) for d, n in zip(domain, counts)) for counts in cfg["tiles"]]
         args.extra = json.dumps(cfg.get("cuda", {}))
         args.budgets = str(cfg.get("cuda", {}).get("SMEM_BUDGET", 110 * 1024) // 1024)
         args.threads = str(cfg.get("cuda", {}).get("THREADS", 256))
     assignment = [int(c) for c in args.assignment]
     shapes = [tuple(int(v) for v in t.split("x")) for t in args.tiles.split(",")]
+    if args.from_tuned:
+        shapes = [tuple(tuned_shapes)]          # the tuned variant: its own tile shape per group
     subtiles = [tuple(int(v) for v in t.split("x")) for t in args.subtiles.split(",") if t] or [None]
     extra = json.loads(args.extra) if args.extra else {}
     sweep = json.loads(args.sweep) if args.sweep else {}
@@ -139,8 +144,9 @@ def main():
         path = os.path.join(ROOT, "absinthe_b200", "tuned.json")
         tuned = json.load(open(path)) if os.path.exists(path) else {}
         best = results[0]
-        counts = [max(1, ceil_div(d, s)) for d, s in zip(domain, best["tile"])]
-        tuned[args.kernel] = {"assignment": assignment, "tiles": [counts] * (max(assignment) + 1),
+        per_group = best["tile"] if isinstance(best["tile"][0], (list, tuple)) else [best["tile"]] * (max(assignment) + 1)
+        tuned[args.kernel] = {"assignment": assignment,
+                              "tiles": [[max(1, ceil_div(d, s)) for d, s in zip(domain, sh)] for sh in per_group],
                               "cuda": best["cuda"], "measured": {k: best[k] for k in ("total_ms", "GBps_total")}}
         with open(path, "w") as handle:
             json.dump(tuned, handle, indent=1)
