@@ -36,6 +36,7 @@ DEFAULTS = {
     "SMEM_BUDGET": 110 * 1024,   # two CTAs per SM
     "LOAD": "tma",               # "tma" | "ldg"
     "SUBTILE": None,             # (BX, BY, BZ) override
+    "GROUPS": None,              # {"<kernel id>": {option: value}}: per-group overrides of the options above
     "FMAD": False,               # False -> -fmad=false: bit-exact with the strict oracle
     "FUSE_HALO": False,          # periodic copies written by the producing kernel
     "INLINE": "none",            # intermediates re-evaluated in registers: "none" | "all" | [names]
@@ -623,12 +624,23 @@ class Plan:
             if not outer["LOOPS"]:
                 continue                      # the dummy input-halo group
             for inner in outer["GROUPS"]:
-                self.groups.append(GroupPlan(program, inner, self.opts))
+                self.groups.append(GroupPlan(program, inner, self._group_options(inner["ID"] + 1)))
         tiling = program["TILING"]
         self.inputs = sorted(tiling["INPUTS"])
         self.outputs = sorted(tiling["OUTPUTS"])
         produced = [n for g in self.groups for n in g.outputs]
         self.temps = sorted(set(produced) - set(self.outputs))
+
+    def _group_options(self, kernel_id):
+        """The options of one group kernel: the program-wide ones, then ``GROUPS[<kernel id>]`` on top
+        (launch shape, staging and sub-tile choices differ between the groups of one variant)."""
+        per_group = self.opts.get("GROUPS") or {}
+        override = per_group.get(str(kernel_id), per_group.get(kernel_id, {}))
+        unknown = set(override) - set(DEFAULTS) | set(override) & {"GROUPS", "FMAD", "WAIT_SLEEP"}
+        assert not unknown, "not a per-group option: %s" % sorted(unknown)
+        opts = dict(self.opts)
+        opts.update(override)
+        return opts
 
     def context(self):
         p = self.program

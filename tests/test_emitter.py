@@ -94,3 +94,19 @@ def test_branchify_leaves_nested_or_cheap_conditionals_alone():
 def test_impossible_shared_memory_plan_is_an_error():
     with pytest.raises(AssertionError):
         plan("fastwaves", [F], [(1, 1, 1)], {"SUBTILE": (256, 64, 60)})
+
+
+def test_per_group_options_override_the_program_wide_ones():
+    seq = P.KERNELS["fastwaves"][1]()
+    program = P.make_program("fastwaves", [seq[:6], seq[6:]], [(2, 8, 4), (1, 4, 6)])
+    program["CUDA"] = {"INLINE": "all", "BLOCK": (1, 2), "THREADS": 384,
+                       "GROUPS": {"2": {"THREADS": 256, "BLOCK": (2, 1), "STAGES": 3}}}
+    g1, g2 = Plan(P.clone(program)).groups
+    assert (g1.threads, g1.block, g1.stages) == (384, (1, 1, 2), 2)
+    assert (g2.threads, g2.block, g2.stages) == (256, (1, 2, 1), 3)
+    text = Plan(P.clone(program)).descriptor_text()
+    assert "group 1 kernel absinthe_group1 threads %d" % (384 + 32) in text
+    assert "group 2 kernel absinthe_group2 threads %d" % (256 + 32) in text
+    program["CUDA"]["GROUPS"] = {"1": {"FMAD": True}}
+    with pytest.raises(AssertionError, match="not a per-group option"):
+        Plan(P.clone(program))

@@ -133,3 +133,14 @@ def test_shipped_variant_groupings_match_oracle(launcher_lib, name, program):
     tuned = P.clone(program)
     tuned["CUDA"] = {"INLINE": "all", "BLOCK": (2, 1), "SHUFFLE": True, "FUSE_HALO": True}
     assert_bit_exact(tuned)
+
+
+def test_per_group_options_match_oracle(launcher_lib):
+    """Every group kernel of a variant may have its own launch shape / staging options."""
+    seq = P.KERNELS["fastwaves"][1]()
+    program = P.make_program("fastwaves", [seq[:4], seq[4:6], seq[6:]], [(2, 4, 3), (1, 8, 2), (4, 2, 6)],
+                             domain=(72, 40, 18))
+    program["CUDA"] = {"INLINE": "all", "FUSE_HALO": True, "BLOCK": (1, 2), "THREADS": 384,
+                       "GROUPS": {"2": {"THREADS": 128, "BLOCK": (2, 1), "SHUFFLE": True, "STAGES": 3},
+                                  "3": {"LOAD": "ldg", "BLOCK": (1, 1), "INLINE": "none"}}}
+    assert_bit_exact(program)
