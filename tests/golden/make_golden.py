@@ -1,6 +1,6 @@
 """Generate tests/golden/* from the REAL reference (development container only).
 
-Run as ``PYTHONHASHSEED=0 python tools/make_golden.py``.  Needs ``/root/reference``; the
+Run as ``PYTHONHASHSEED=0 python tests/golden/make_golden.py``.  Needs ``/root/reference``; the
 fixtures it writes are small and committed, so the tests that use them run anywhere:
 
 * ``stencil_fingerprints.json``  whitespace-insensitive sha256 prefix of every stencil string of
@@ -21,7 +21,7 @@ import os
 import random
 import sys
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 REFERENCE = "/root/reference"

@@ -1,5 +1,5 @@
 """The analyzer reproduces the reference's variant description (fixtures from the real
-stencil_analyzer.py, see tools/make_golden.py) plus the tile geometry rules."""
+stencil_analyzer.py, see tests/golden/make_golden.py) plus the tile geometry rules."""
 
 import json
 import os

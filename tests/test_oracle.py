@@ -1,5 +1,5 @@
 """The oracle against the reference: committed digests of reference-computed inputs/outputs
-(tools/make_golden.py), and -- where the reference sources are mounted -- the live
+(tests/golden/make_golden.py), and -- where the reference sources are mounted -- the live
 compute_reference of the reference's own generated program."""
 
 import json
