@@ -1,39 +1,71 @@
 #!/usr/bin/env python
 """Interleaved A/B timing of CUDA option sets on one tuned variant (removes warm-up / power-state order bias).
-usage: ab_test.py <kernel> '<json options A>' '<json options B>' ...
+
+    ab_test.py [--prebuild] <kernel> '<json options A>' '<json options B>' ...
+
 An option set may hold "_shapes": [[x, y, z], ...] -- tile shapes in points, one per group (or one for all) --
-which replaces the tuned tile counts.  Prints the median per variant and per group."""
-import json, os, statistics, sys
+which replaces the tuned tile counts, and "GROUPS": {"<kernel id>": {...}} for per-group options.  Prints the
+median per variant and per group kernel.  ``--prebuild`` only compiles the candidates (in parallel, no GPU
+needed) so that the variant cache travels to the GPU box with the snapshot.
+"""
+import json
+import os
+import statistics
+import sys
+from concurrent.futures import ProcessPoolExecutor
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import torch
-from absinthe_b200 import programs as P
-from absinthe_b200.launcher import Variant, make_periodic
+DOMAIN = (1024, 1024, 80)
+
+
+def candidate(kernel, extra):
+    """The tuned program of ``kernel`` with the option set ``extra`` applied."""
+    from absinthe_b200 import programs as P
+    cfg = json.load(open(os.path.join(ROOT, "absinthe_b200", "tuned.json")))[kernel]
+    groups = P.split_sequence(P.KERNELS[kernel][1](), cfg["assignment"])
+    extra = dict(extra)
+    tiles = [tuple(t) for t in cfg["tiles"]]
+    shapes = extra.pop("_shapes", None)
+    if shapes:
+        shapes = shapes * len(groups) if len(shapes) == 1 else shapes
+        tiles = [tuple(-(-d // s) for d, s in zip(DOMAIN, shape)) for shape in shapes]
+    program = P.make_program(kernel, groups, tiles, domain=DOMAIN)
+    program["CUDA"] = dict(cfg["cuda"])
+    program["CUDA"].update(extra)
+    return program
+
+
+def prebuild(job):
+    from absinthe_b200.generator import build_variant
+    try:
+        return build_variant(candidate(*job))[1]
+    except Exception as exc:
+        return "FAILED %s: %s" % (json.dumps(job[1]), str(exc)[-300:])
+
 
 def main():
-    kernel = sys.argv[1]
-    overrides = [json.loads(a) for a in sys.argv[2:]]
-    cfg = json.load(open(os.path.join(ROOT, "absinthe_b200", "tuned.json")))[kernel]
-    seq = P.KERNELS[kernel][1]()
+    args = sys.argv[1:]
+    build_only = "--prebuild" in args
+    args = [a for a in args if a != "--prebuild"]
+    kernel, overrides = args[0], [json.loads(a) for a in args[1:]]
+    if build_only:
+        with ProcessPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+            for line in pool.map(prebuild, [(kernel, extra) for extra in overrides]):
+                print(line)
+        return
+    import torch
+    from absinthe_b200.launcher import Variant, make_periodic
     variants, tensors = [], {}
     gen = torch.Generator(device="cuda").manual_seed(7)
-    domain = (1024, 1024, 80)
-    groups = P.split_sequence(seq, cfg["assignment"])
     for extra in overrides:
-        extra = dict(extra)
-        tiles = [tuple(t) for t in cfg["tiles"]]
-        shapes = extra.pop("_shapes", None)
-        if shapes:
-            shapes = shapes * len(groups) if len(shapes) == 1 else shapes
-            tiles = [tuple(-(-d // s) for d, s in zip(domain, shape)) for shape in shapes]
-        program = P.make_program(kernel, groups, tiles, domain=domain)
-        program["CUDA"] = dict(cfg["cuda"]); program["CUDA"].update(extra)
-        v = Variant.from_program(program)
+        v = Variant.from_program(candidate(kernel, extra))
         dims = (v.X, v.Y, v.Z, v.HX, v.HY, v.HZ)
         for n in v.inputs + v.outputs:
             if n not in tensors:
                 t = torch.rand(v.shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5
-                make_periodic(t, dims); tensors[n] = t
+                make_periodic(t, dims)
+                tensors[n] = t
         v.bind([tensors[n] for n in v.inputs], [tensors[n] for n in v.outputs])
         variants.append(v)
     samples = [[] for _ in variants]
@@ -45,7 +77,9 @@ def main():
             for _ in range(4):
                 for g in range(1, v.n_groups + 1):
                     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                    a.record(); v.apply_group(g); b.record()
+                    a.record()
+                    v.apply_group(g)
+                    b.record()
                     events.append((g, a, b))
             torch.cuda.synchronize()
             if rnd >= 2:
@@ -56,6 +90,7 @@ def main():
         print("%-60s median %.4f ms  min %.4f  groups %s" % (
             json.dumps(extra), statistics.median(s), min(s),
             " ".join("%.4f" % statistics.median(g) for g in groups_ms)), flush=True)
+
 
 if __name__ == "__main__":
     main()
