@@ -28,6 +28,7 @@ SYMBOLS = [
     "absinthe_halo_pack", "absinthe_halo_unpack", "absinthe_make_periodic_ik",
     "absinthe_variant_pack_group", "absinthe_variant_unpack_group",
     "absinthe_variant_apply_host_async", "absinthe_variant_wait_host", "absinthe_compare_fields",
+    "absinthe_variant_host_interior",
 ]
 
 
@@ -75,6 +76,7 @@ def load_library(path=None):
                                                 c.c_void_p]
     lib.absinthe_variant_apply_host_async.argtypes = lib.absinthe_variant_apply_host.argtypes
     lib.absinthe_variant_wait_host.argtypes = [c.c_void_p]
+    lib.absinthe_variant_host_interior.argtypes = [c.c_void_p, c.c_int]
     lib.absinthe_compare_fields.argtypes = [c.c_void_p, c.c_void_p] + [c.c_int] * 6 + [
         c.c_double, c.POINTER(c.c_ulonglong), c.POINTER(c.c_ulonglong), c.c_void_p]
     lib.absinthe_make_periodic.argtypes = [c.c_void_p] + [c.c_int] * 6 + [c.c_void_p]
@@ -227,6 +229,10 @@ class Variant:
                            _pointer_array([t.data_ptr() for t in host_outputs]), _stream_handle(stream)),
               "apply_host")
         self._host = (self._host + [(host_inputs, host_outputs)])[-2:]   # keep the buffers of steps in flight alive
+
+    def host_interior(self, enable=True):
+        """Upload only the interiors of host inputs; the library rebuilds their periodic halos on the device."""
+        check(self.lib, self.lib.absinthe_variant_host_interior(self.handle, int(enable)), "host_interior")
 
     def wait_host(self):
         check(self.lib, self.lib.absinthe_variant_wait_host(self.handle), "wait_host")

@@ -418,11 +418,13 @@ def run_gpu_arm(args):
         t = torch.tensor([e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
-    h2d = sum(sum(1 for t in hin if t is not None) for _, hin, _, _ in host) * host[0][0].field_bytes
+    # bytes that cross the bus per uploaded field: its interior, or the whole padded field
+    up_bytes = points * 8 if args.e2e_upload == "interior" else host[0][0].field_bytes
+    h2d = sum(sum(1 for t in hin if t is not None) for _, hin, _, _ in host) * up_bytes
     d2h = sum(len(hout[0]) for _, _, hout, _ in host) * host[0][0].field_bytes
     e2e = {"value": round(2 * points * world / (e2e_ms * 1e-3) / 1e6, 1), "unit": "Mpoints/s",
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": round(e2e_ms, 2),
-           "steps": e2e_steps, "constants_resident": constants, "steps_in_flight": depth,
+           "steps": e2e_steps, "constants_resident": constants, "steps_in_flight": depth, "upload": args.e2e_upload,
            "api": "Variant.apply_host(wait=False) + wait_host per sequence and step "
                   "(absinthe_variant_apply_host_async / absinthe_variant_wait_host)"}
 
@@ -470,6 +472,9 @@ def main():
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="absinthe_b200", choices=["absinthe_b200", "reference"])
     parser.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    parser.add_argument("--e2e-upload", default="full", choices=["full", "interior"],
+                        help="end-to-end leg: upload whole padded fields, or only the interiors of the host inputs "
+                             "(the library rebuilds their periodic halos on the device; measured: same step time)")
     args = parser.parse_args()
     claim_stdout()
     if args.impl == "reference":

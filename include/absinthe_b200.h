@@ -118,6 +118,12 @@ int absinthe_variant_apply_host_async(absinthe_variant* v, const double* const* 
                                       double* const* h_outputs, void* stream);
 int absinthe_variant_wait_host(absinthe_variant* v);
 
+/* Host-upload mode of the two calls above.  enable != 0: only the X*Y*Z interior of every host input
+ * crosses the bus (pitched 3-D copy, 8 % fewer bytes at 1024x1024x80) and the periodic halo is rebuilt on
+ * the device by the library -- identical to the default as long as the host halos were periodic, which
+ * the reference's main() guarantees (template_tiling.cpp:209-221).  Default 0: whole padded fields. */
+int absinthe_variant_host_interior(absinthe_variant* v, int enable);
+
 /* ---- field helpers ----------------------------------------------------------------------- */
 
 /* periodic boundary condition on a device field (i, then j, then k faces; corners consistent) */

@@ -170,3 +170,30 @@ def test_two_host_steps_in_flight(launcher_lib):
     for got, want in zip(outs[1], steps[1][1]):
         assert torch.equal(got, want)
     v.close()
+
+
+def test_interior_upload_rebuilds_the_halos(launcher_lib):
+    """host_interior: only interiors cross the bus, the periodic halos of the inputs are rebuilt on the device."""
+    program = P.make_program("advection", None, [(2, 4, 3)], domain=(70, 33, 11))
+    inputs, _ = make_inputs(program, seed=9)
+    want = run(program, inputs)
+    v = Variant.from_program(P.clone(program))
+    v.bind([v.empty_field() for _ in v.inputs], [v.empty_field() for _ in v.outputs])
+    v.host_interior(True)
+    host_in = []
+    for name in v.inputs:
+        h = inputs[name].cpu()
+        spoiled = torch.full_like(h, 1e300)                  # whatever the caller left in the halos is ignored
+        spoiled[3:-3, 3:-3, 3:-3] = h[3:-3, 3:-3, 3:-3]
+        host_in.append(spoiled.pin_memory())
+    for wait in (True, False):
+        host_out = [torch.zeros(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
+        v.apply_host(host_in, host_out, wait=wait)
+        v.wait_host()
+        for name, t in zip(v.outputs, host_out):
+            assert torch.equal(t, want[name].cpu()), (wait, name)
+    v.host_interior(False)                                   # back to whole fields: the spoiled halos now count
+    host_out = [torch.zeros(v.shape, dtype=torch.float64).pin_memory() for _ in v.outputs]
+    v.apply_host(host_in, host_out)
+    assert any(not torch.equal(t, want[name].cpu()) for name, t in zip(v.outputs, host_out))
+    v.close()
