@@ -103,13 +103,13 @@ def explore_space(kernel, experiments, folder):
             out.writerow([program["VARIANT"], str(program["OBJECTIVE"])])
 
 
-def training_experiments(family, cores=P.B200_SMS):
+def training_experiments(family, cores=P.B200_SMS, stride=20):
     """All (variant, tile shape) training programs (ref fitcache.py:116-172, fitddr.py:187-327)."""
     variants = S.FITCACHE_VARIANTS if family == "fitcache" else S.FITDDR_VARIANTS
     experiments = {}
     for variant in variants:
         for shape in P.training_tile_shapes():
-            program = P.training_program(family, variant, shape, cores)
+            program = P.training_program(family, variant, shape, cores, stride)
             domain = "%dx%dx%d" % (program["X"], program["Y"], program["Z"])
             experiments["%s-%s" % (variant, domain)] = program
     return experiments
@@ -119,10 +119,11 @@ def main(kernel, arguments):
     """Entry point of the root-level scripts."""
     training = kernel in ("fitcache", "fitddr")
     optimize = explore = auto = generate = build = False
-    parse, folder = None, "./"
+    parse, folder, stride = None, "./", 20
     try:
-        short = "gbvp:f:" if training else "oeagbp:f:"
-        extended = (["generate", "build", "verify", "parse=", "folder="] if training else
+        # -s/--stride is an addition: execute every N-th training tile (reference protocol: 20)
+        short = "gbvp:f:s:" if training else "oeagbp:f:"
+        extended = (["generate", "build", "verify", "parse=", "folder=", "stride="] if training else
                     ["optimize", "explore", "auto", "generate", "build", "parse=", "folder="])
         opts, _ = getopt(arguments, short, extended)
     except GetoptError:
@@ -143,13 +144,15 @@ def main(kernel, arguments):
             parse = arg
         elif opt in ("-f", "--folder"):
             folder = os.path.normpath(arg) + "/"
+        elif opt in ("-s", "--stride"):
+            stride = int(arg)
     print("-> working dir: " + str(folder))
     print("-> run generation: " + str(generate))
     print("-> run compilation: " + str(build))
     os.makedirs(folder, exist_ok=True)
     experiments = {}
     if training:
-        experiments = training_experiments(kernel)
+        experiments = training_experiments(kernel, stride=stride)
         template, cores = "template_training.cu", P.B200_SMS
     else:
         template, cores = "template_tiling.cu", P.base_program(kernel)["MACHINE"]["CORES"]

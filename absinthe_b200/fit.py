@@ -63,18 +63,20 @@ def _with_intercept(design, intercept):
     return np.concatenate([design, np.ones((len(design), 1))], axis=1) if intercept else design
 
 
-def fit_cache(rows, cores, nonnegative=False, intercept=False):
+def fit_cache(rows, cores, nonnegative=False, intercept=False, tiles_per_core=1):
     """``{"BODY", "PEEL"}`` from a fitcache sweep (ref fitcache.R:27-50; PT8 is excluded, ``fac >= 10``).
 
     ``intercept`` adds a constant column: on a GPU one wave of small tiles is dominated by the launch
-    and pipeline-fill latency, which the reference's through-the-origin model cannot express."""
+    and pipeline-fill latency, which the reference's through-the-origin model cannot express.
+    ``tiles_per_core``: tiles every core executed per run (20 / STRIDE of the training programs); the
+    measured time is divided by it, so the regressors stay per-tile as in the reference."""
     fac = np.array([float(r[0][2:]) for r in rows])
     keep = fac >= 10
     rows = [r for r, k in zip(rows, keep) if k]
     fac = fac[keep]
     t = _tile_terms(rows, cores)
     design = _with_intercept(np.stack([fac * STEPS * t["XYZ"], fac * STEPS * t["YZ"]], axis=1), intercept)
-    target = np.array([r[4] for r in rows])
+    target = np.array([r[4] for r in rows]) / tiles_per_core
     coef = lad(design, target, nonnegative)
     out = {"BODY": coef[0] / cores, "PEEL": coef[1] / cores, "R2": r_squared(design, target, coef),
            "SAMPLES": len(rows)}
@@ -83,7 +85,7 @@ def fit_cache(rows, cores, nonnegative=False, intercept=False):
     return out
 
 
-def fit_ddr(rows, cores, nonnegative=False, intercept=False):
+def fit_ddr(rows, cores, nonnegative=False, intercept=False, tiles_per_core=1):
     """``{"RW BODY", "ST BODY", "RW PEEL", "ST PEEL"}`` from a fitddr sweep (ref fitddr.R:27-56)."""
     inp = np.array([float(r[0][2]) for r in rows])
     keep = inp >= 1
@@ -96,7 +98,7 @@ def fit_ddr(rows, cores, nonnegative=False, intercept=False):
     rw_peel = STEPS * t["YZ"]
     st_peel = STEPS * (inp + 1) * t["YZ"] + STEPS * inp * bd * (t["Y"] + t["Z"])
     design = _with_intercept(np.stack([rw_body, st_body, rw_peel, st_peel], axis=1), intercept)
-    target = np.array([r[4] for r in rows])
+    target = np.array([r[4] for r in rows]) / tiles_per_core
     coef = lad(design, target, nonnegative)
     names = ("RW BODY", "ST BODY", "RW PEEL", "ST PEEL")
     out = {n: c / cores for n, c in zip(names, coef)}
@@ -139,12 +141,16 @@ def main(argv=None):
     ap.add_argument("--cores", type=int, default=148)
     ap.add_argument("--nonnegative", action="store_true")
     ap.add_argument("--intercept", action="store_true", help="fit a constant launch-latency term as well")
+    ap.add_argument("--tiles-per-core", type=float, default=1.0,
+                    help="tiles each core executed per run: 20 / the --stride the sweep was generated with")
     args = ap.parse_args(argv)
     out = {}
     if args.cache:
-        out["CACHE"] = fit_cache(load_results(args.cache), args.cores, args.nonnegative, args.intercept)
+        out["CACHE"] = fit_cache(load_results(args.cache), args.cores, args.nonnegative, args.intercept,
+                                 args.tiles_per_core)
     if args.ddr:
-        out["MEMORY"] = fit_ddr(load_results(args.ddr), args.cores, args.nonnegative, args.intercept)
+        out["MEMORY"] = fit_ddr(load_results(args.ddr), args.cores, args.nonnegative, args.intercept,
+                                args.tiles_per_core)
     print(json.dumps(out, indent=1))
 
 

@@ -119,8 +119,12 @@ def training_tile_shapes():
             if 500 <= x * y * z <= 2000]
 
 
-def training_program(family, variant, shape, cores=B200_SMS):
-    """One training program: 2 x 2 x (5*cores) tiles of ``shape`` points, all nine stencils fused."""
+def training_program(family, variant, shape, cores=B200_SMS, stride=20):
+    """One training program: 2 x 2 x (5*cores) tiles of ``shape`` points, all nine stencils fused.
+
+    Every ``stride``-th tile is executed: 20 is the reference's protocol (one tile per core, ref
+    template_training.cpp:276-311); 1 runs all 20 tiles per core back to back, which on a GPU measures
+    the per-tile cost at throughput instead of one launch latency (fit with ``--tiles-per-core 20``)."""
     xlen, ylen, zlen = shape
     if family == "fitcache":
         table, sequence = S.fitcache_stencils(variant), S.fitcache_sequence()
@@ -139,7 +143,7 @@ def training_program(family, variant, shape, cores=B200_SMS):
         "VARIANT": variant,
         "STENCILS": table, "SEQUENCE": sequence,
         "TILING": tiling_from_groups([sequence], [(2, 2, 5 * cores)]),
-        "TRAINING": {"CORES": cores, "STRIDE": 20},
+        "TRAINING": {"CORES": cores, "STRIDE": int(stride)},
     }
     return program
 

@@ -55,6 +55,17 @@ def test_training_drivers_enumerate_the_reference_sweep():
     assert (p["X"], p["Y"], p["Z"]) == (100, 10, 60) and p["TILING"]["GROUPS"][0]["GROUPS"][0]["NZ"] == 20
 
 
+def test_training_stride_option(tmp_path):
+    """-s/--stride: every N-th tile is executed (20 = the reference's one-tile-per-core protocol)."""
+    from absinthe_b200 import generator as G
+    default = driver.training_experiments("fitcache", cores=4)["PT12-100x10x60"]
+    assert default["TRAINING"]["STRIDE"] == 20
+    full = driver.training_experiments("fitcache", cores=4, stride=1)["PT12-100x10x60"]
+    assert full["TRAINING"]["STRIDE"] == 1
+    G.generate_code("template_training.cu", str(tmp_path / "t.cu"), full)
+    assert " training_step 1 " in (tmp_path / "t.desc").read_text()
+
+
 def test_root_scripts_run(tmp_path):
     out = subprocess.run([sys.executable, os.path.join(ROOT, "fitcache.py"), "-f", str(tmp_path)],
                          capture_output=True, text=True, cwd=ROOT)

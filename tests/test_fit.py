@@ -52,6 +52,11 @@ def test_ddr_design_matches_reference_formula():
     for key, value in true.items():
         assert got[key] == pytest.approx(value, rel=1e-5)
     assert got["SAMPLES"] == 25           # IN0BD0 is not trained on (ref fitddr.R:40)
+    # a sweep that ran all 20 tiles per core (--stride 1) measures 20 x the per-tile time
+    full = [r[:4] + (20 * r[4],) for r in rows]
+    again = fit.fit_ddr(full, cores, tiles_per_core=20)
+    for key, value in true.items():
+        assert again[key] == pytest.approx(value, rel=1e-5)
 
 
 def test_spearman():
