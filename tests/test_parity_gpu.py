@@ -68,16 +68,18 @@ def test_cuda_graph_replay(launcher_lib):
 
 @pytest.mark.parametrize("family,variant", [("fitcache", "PT12"), ("fitcache", "PT20"), ("fitddr", "IN0BD0"),
                                             ("fitddr", "IN2BD1"), ("fitddr", "IN3BD2")])
-def test_training_protocol_matches_oracle_on_selected_tiles(launcher_lib, family, variant):
+@pytest.mark.parametrize("stride", [20, 1, 7])
+def test_training_protocol_matches_oracle_on_selected_tiles(launcher_lib, family, variant, stride):
     """Training mode evaluates tiles 0, 20, 40, ... only (ref template_training.cpp:277-278): those tiles
-    must carry the oracle's values, every other cell of the outputs must stay untouched."""
+    must carry the oracle's values, every other cell of the outputs must stay untouched.  Other strides
+    (``fitcache.py -s N``; 1 = every tile) select their own tiles."""
     import numpy as np
     import torch
     from absinthe_b200.emitter import tile_geometry
     from absinthe_b200.launcher import Variant
     from common import run_oracle
     cores = 3
-    program = P.training_program(family, variant, (10, 3, 4), cores=cores)
+    program = P.training_program(family, variant, (10, 3, 4), cores=cores, stride=stride)
     oracle, inputs, expected = run_oracle(program)
     v = Variant.from_program(P.clone(program), "template_training.cu")
     by_name = dict(zip(oracle.inputs, inputs))
@@ -90,12 +92,12 @@ def test_training_protocol_matches_oracle_on_selected_tiles(launcher_lib, family
     dims = (v.X, v.Y, v.Z)
     geo = [tile_geometry(s, n) for s, n in zip(dims, counts)]
     mask = np.zeros(v.shape, dtype=bool)
-    for tile in range(0, counts[0] * counts[1] * counts[2], 20):
+    for tile in range(0, counts[0] * counts[1] * counts[2], stride):
         t = (tile % counts[0], (tile // counts[0]) % counts[1], tile // (counts[0] * counts[1]))
         lo = [max(0, c * g[0] + g[1]) for c, g in zip(t, geo)]
         hi = [min(s, (c + 1) * g[0] + g[1]) for c, g, s in zip(t, geo, dims)]
         mask[3 + lo[2]:3 + hi[2], 3 + lo[1]:3 + hi[1], 3 + lo[0]:3 + hi[0]] = True
-    assert mask.sum() == cores * 10 * 3 * 4
+    assert mask.sum() == len(range(0, 20 * cores, stride)) * 10 * 3 * 4
     for name, want in zip(oracle.outputs, expected):
         got = outs[v.outputs.index(name)].cpu().numpy()
         assert np.array_equal(got[mask], want[mask]), name
