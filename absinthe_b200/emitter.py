@@ -46,6 +46,9 @@ DEFAULTS = {
     "BRANCH": False,             # expensive ?: arms become real (warp-coherent) branches
     "STORE_CS": False,           # outputs written with the evict-first (streaming) cache hint
     "L2_ONCE": False,            # centre-only inputs are staged with an L2 evict-first policy
+    "UNIFORM_WARP": False,       # warp index through __shfl_sync(.., 0): the compiler then knows that the role
+                                 # split and the per-warp task loops are warp-uniform (uniform datapath, no
+                                 # re-materialised descriptors in "divergent" code)
     "WAIT_SLEEP": 0,             # ns a starved consumer backs off between mbarrier polls
     "L2_PREFETCH": 0,            # work items whose boxes are prefetched into L2 ahead of the ring
     "STREAM_K": False,           # walk a tile column plane by plane through a ring of k-planes
@@ -607,7 +610,7 @@ class GroupPlan:
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
             "BLOCK": self.block, "FUSE_HALO": self.fuse_halo, "FRONT": self.front,
             "WARPS": self.threads // 32, "LAUNCH_THREADS": self.launch_threads,
-            "STREAM_STORES": bool(self.opts["STORE_CS"]), "L2_PREFETCH": int(self.opts["L2_PREFETCH"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
+            "STREAM_STORES": bool(self.opts["STORE_CS"]), "UNIFORM_WARP": bool(self.opts["UNIFORM_WARP"]), "L2_PREFETCH": int(self.opts["L2_PREFETCH"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
             "FIRST_BYTES": getattr(self, "first_bytes", 0), "NB": self.stages,
         }
 

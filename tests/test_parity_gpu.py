@@ -34,6 +34,9 @@ OPTIONS = [
     ("branch", {"INLINE": "all", "BRANCH": True, "BLOCK": (2, 1), "FUSE_HALO": True}),
     ("cache-hints", {"INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "STORE_CS": True, "L2_ONCE": True,
                      "L2_PREFETCH": 3}),
+    ("uniform-warp", {"INLINE": "all", "SHUFFLE": True, "BLOCK": (2, 1), "FUSE_HALO": True, "UNIFORM_WARP": True}),
+    ("uniform-warp-stream-k", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True,
+                               "UNIFORM_WARP": True}),
     ("stream-k", {"STREAM_K": True}),
     ("stream-k-inline", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "PREFETCH": 1}),
     ("stream-k-shuffle", {"STREAM_K": True, "INLINE": "all", "BLOCK": (3, 1), "SHUFFLE": True, "FUSE_HALO": True,
