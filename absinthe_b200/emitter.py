@@ -46,6 +46,9 @@ DEFAULTS = {
     "BRANCH": False,             # expensive ?: arms become real (warp-coherent) branches
     "STORE_CS": False,           # outputs written with the evict-first (streaming) cache hint
     "L2_ONCE": False,            # centre-only inputs are staged with an L2 evict-first policy
+    "POLL_WARP": False,          # EXPERIMENTAL, compiles but has not run on hardware yet (no GPU parity case): only
+                                 # warp 0 polls the full-barrier of a stage, the other consumer warps sleep in a
+                                 # named barrier behind it (fewer issue slots burnt on polling)
     "UNIFORM_WARP": False,       # warp index through __shfl_sync(.., 0): the compiler then knows that the role
                                  # split and the per-warp task loops are warp-uniform (uniform datapath, no
                                  # re-materialised descriptors in "divergent" code)
@@ -610,7 +613,7 @@ class GroupPlan:
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
             "BLOCK": self.block, "FUSE_HALO": self.fuse_halo, "FRONT": self.front,
             "WARPS": self.threads // 32, "LAUNCH_THREADS": self.launch_threads,
-            "STREAM_STORES": bool(self.opts["STORE_CS"]), "UNIFORM_WARP": bool(self.opts["UNIFORM_WARP"]), "L2_PREFETCH": int(self.opts["L2_PREFETCH"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
+            "STREAM_STORES": bool(self.opts["STORE_CS"]), "UNIFORM_WARP": bool(self.opts["UNIFORM_WARP"]), "POLL_WARP": bool(self.opts["POLL_WARP"]), "L2_PREFETCH": int(self.opts["L2_PREFETCH"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
             "FIRST_BYTES": getattr(self, "first_bytes", 0), "NB": self.stages,
         }
 
