@@ -27,7 +27,10 @@ The plan also yields the launcher descriptor (``descriptor_text``): fields,
 kernels, launch shapes, parameter-block layout, halo lists.
 """
 
+import re
+
 from . import analysis as A
+from . import column
 
 SMEM_LIMIT = 227 * 1024          # opt-in maximum per CTA on sm_100a
 DEFAULTS = {
@@ -54,7 +57,10 @@ DEFAULTS = {
                                  # re-materialised descriptors in "divergent" code)
     "WAIT_SLEEP": 0,             # ns a starved consumer backs off between mbarrier polls
     "L2_PREFETCH": 0,            # work items whose boxes are prefetched into L2 ahead of the ring
-    "STREAM_K": False,           # walk a tile column plane by plane through a ring of k-planes
+    "STREAM_K": False,           # True: walk a tile column plane by plane through rings of k-planes in shared
+                                 # memory; "regs": column kernel (column.py) -- a thread owns a column, values
+                                 # wanted again at lower planes are carried in registers, no CTA barriers
+    "COLUMN": None,              # column kernel shape: {"WARPS": (WX, WY), "PLANES": planes per TMA box, "SLOTS": ring}
     "PREFETCH": 2,               # STREAM_K: input planes in flight beyond the ones being read
 }
 FRONT_SLACK = 16                 # doubles before the first box (halo lanes of a warp read below it)
@@ -166,9 +172,12 @@ class GroupPlan:
     ``__syncthreads()`` where one reads what another wrote.
     """
 
-    def __init__(self, program, group, opts):
+    column = False
+
+    def __init__(self, program, group, opts, kernel_name=None):
         self.program, self.group, self.opts = program, group, opts
         self.id = group["ID"] + 1          # kernel numbering follows the outer (schedule) id
+        self.kernel_name = kernel_name or "absinthe_group%d" % self.id
         self.stencils = group["STENCILS"]
         self.names = [s["NAME"] for s in self.stencils]
         self.by_name = {s["NAME"]: s for s in self.stencils}
@@ -192,7 +201,7 @@ class GroupPlan:
             self.load = "ldg"              # TMA needs 16-byte global strides
         self.stages = opts["STAGES"] if self.load == "tma" else 1
         self.threads = opts["THREADS"]
-        self.stream = bool(opts["STREAM_K"]) and self.load == "tma" and self.block[2] == 1
+        self.stream = bool(opts["STREAM_K"]) and opts["STREAM_K"] != "regs" and self.load == "tma" and self.block[2] == 1
         if self.stream:
             # k-streaming: one work item is a (bx, by) column over the whole k-range of its tile.  Plane g
             # of every staged input travels together in ring slot g mod R; a phase whose results are read
@@ -251,7 +260,7 @@ class GroupPlan:
                 keep.append(n)
         self.in_smem = keep
         centre_only = [n for n in self.inputs if self.reach[n] == A.ZERO_BOX]
-        direct = "none" if self.opts["STREAM_K"] else self.opts["DIRECT"]
+        direct = "none" if self.opts["STREAM_K"] not in (False, None, "regs") else self.opts["DIRECT"]
         self.direct = self._select("all" if direct == "auto" else direct, centre_only)
         self.staged = [n for n in self.inputs if n not in self.direct]
 
@@ -599,7 +608,7 @@ class GroupPlan:
 
     def context(self):
         return {
-            "ID": self.id, "KERNEL": "absinthe_group%d" % self.id,
+            "ID": self.id, "KERNEL": self.kernel_name,
             "THREADS": self.threads, "STAGES": self.stages, "TMA": self.load == "tma",
             "T": self.T, "O": self.O, "N": self.N, "B": self.B, "NSUB": self.nsub,
             "NSUB_TOTAL": self.nsub[0] * self.nsub[1] * self.nsub[2],
@@ -630,7 +639,13 @@ class Plan:
             if not outer["LOOPS"]:
                 continue                      # the dummy input-halo group
             for inner in outer["GROUPS"]:
-                self.groups.append(GroupPlan(program, inner, self._group_options(inner["ID"] + 1)))
+                opts = self._group_options(inner["ID"] + 1)
+                # kernels carry the sequence's name so that launch lists attribute them (absinthe_<name>_g<id>)
+                symbol = "absinthe_%s_g%d" % (re.sub(r"\W", "_", str(program.get("NAME", "variant"))), inner["ID"] + 1)
+                if opts["STREAM_K"] == "regs" and column.applicable(program, inner, opts):
+                    self.groups.append(column.ColumnPlan(program, inner, opts, symbol))
+                else:
+                    self.groups.append(GroupPlan(program, inner, opts, symbol))
         tiling = program["TILING"]
         self.inputs = sorted(tiling["INPUTS"])
         self.outputs = sorted(tiling["OUTPUTS"])
@@ -676,9 +691,9 @@ class Plan:
         for name in self.temps:
             lines.append("field %s tmp" % name)
         for g in self.groups:
-            lines.append("group %d kernel absinthe_group%d threads %d smem %d tiles %d params %d "
+            lines.append("group %d kernel %s threads %d smem %d tiles %d params %d "
                          "training_step %d fused_halo %d" % (
-                             g.id, g.id, g.launch_threads, g.smem_bytes, g.tiles, g.params_bytes,
+                             g.id, g.kernel_name, g.launch_threads, g.smem_bytes, g.tiles, g.params_bytes,
                              training.get("STRIDE", 20), int(g.fuse_halo)))
             for kind, off, name, dim in g.args:
                 if kind == "tmap":

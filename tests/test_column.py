@@ -1,0 +1,85 @@
+"""The column planner (absinthe_b200/column.py): k-leads, thread-local rows, register carries and
+shuffle lanes of every group of the program zoo, verified by replaying the step program on symbolic
+tags (ColumnPlan.simulate) -- no GPU needed.  The GPU parity cases are in test_parity_gpu.py."""
+
+import subprocess
+
+import pytest
+
+from absinthe_b200 import programs as P
+from absinthe_b200.column import ColumnPlan
+from absinthe_b200.emitter import Plan
+from absinthe_b200.generator import nvcc_command, render
+from common import zoo
+
+F = P.KERNELS["fastwaves"][1]()
+SHAPES = [
+    ("default", {}),
+    ("rj2-planes2", {"BLOCK": (2, 1), "COLUMN": {"WARPS": (1, 2), "PLANES": 2}, "FUSE_HALO": True}),
+    ("rj3-planes3", {"BLOCK": (3, 1), "COLUMN": {"WARPS": (2, 1), "PLANES": 3, "SLOTS": 2, "UNROLL": 1}}),
+    ("rj4", {"BLOCK": (4, 1), "COLUMN": {"WARPS": (1, 1)}, "BRANCH": True}),
+]
+
+
+def column_groups(program, cuda):
+    q = P.clone(program)
+    q["CUDA"] = dict(cuda, STREAM_K="regs")
+    return Plan(q).groups
+
+
+@pytest.mark.parametrize("label,cuda", SHAPES, ids=[s[0] for s in SHAPES])
+@pytest.mark.parametrize("name,program", zoo(), ids=[c[0] for c in zoo()])
+def test_step_program_holds_the_right_cells(name, program, label, cuda):
+    groups = column_groups(program, cuda)
+    if program["X"] % 2:
+        assert not any(g.column for g in groups)      # odd rows cannot be TMA sources: classic kernel
+        return
+    for g in groups:
+        assert isinstance(g, ColumnPlan)
+        assert g.simulate() == len(g.outputs) * g.rj * g.useful * (4 - g.kmin)
+        assert g.smem_bytes <= 227 * 1024 and g.kmin <= 0
+
+
+def test_fastwaves_schedule():
+    """ref fastwaves.py:16-48: ppgc reads ppgk(k+1), udc/vdc read uout/vout(k-1), div reads udc/vdc(k+1)."""
+    g = column_groups(P.make_program("fastwaves", [F], [(2, 4, 1)]), {"BLOCK": (2, 1)})[0]
+    assert g.lead == {"ppgk": 2, "ppgc": 1, "ppgu": 1, "ppgv": 1, "uout": 1, "vout": 1, "udc": 1, "vdc": 1, "div": 0}
+    assert g.qtop["ppuv"] == 2 and g.qtop["rho"] == 1 and g.qtop["dzdx"] == 0
+    assert g.kmin == -4                                   # ppuv(k-2) enters at its newest plane k+2
+    # ppgv(j) needs ppgc(j+1); div(j) needs vout(j-1): the v-chain is evaluated on one extra row below
+    assert g.rows["vout"] == [-1, 0, 1] and g.rows["ppgc"] == [-1, 0, 1, 2] and g.rows["uout"] == [0, 1]
+    assert (g.first, g.last) == (1, 30)                   # uout(i-1) and ppgc(i+1) come from the neighbour lanes
+    # every stencil is evaluated once per row and step: nothing is recomputed along k
+    evals = [op for op in g.ops if op[0] == "eval"]
+    assert len(evals) == sum(len(g.rows[n]) for n in g.names)
+    body = "\n".join(g._body())
+    assert "__shfl_up_sync" in body and "__shfl_down_sync" in body and "c_uout_0_0_q0" in g.carried
+
+
+def test_groups_without_k_dependence_carry_nothing():
+    d = P.KERNELS["diffusion"][1]()
+    g = column_groups(P.make_program("diffusion", [d], [(2, 2, 15)]), {"BLOCK": (2, 1)})[0]
+    assert set(g.lead.values()) == {0} and g.carried == [] and g.kmin == 0
+    assert g.rows["ulap"] == [-1, 0, 1, 2] and g.rows["uflj"] == [-1, 0, 1]   # uout reads uflj(j-1), uflj reads ulap(j+1)
+
+
+def test_unrelated_options_fall_back_to_the_classic_kernel():
+    q = P.make_program("fastwaves", [F], [(2, 4, 6)])
+    q["CUDA"] = {"STREAM_K": "regs", "LOAD": "ldg"}
+    assert not Plan(q).groups[0].column
+
+
+@pytest.mark.parametrize("cuda", [SHAPES[1][1], SHAPES[2][1]], ids=["rj2", "rj3"])
+def test_column_kernel_compiles_for_sm_100a(tmp_path, cuda):
+    q = P.make_program("fastwaves", [F], [(2, 4, 2)])
+    q["CUDA"] = dict(cuda, STREAM_K="regs")
+    source, descriptor, flags = render("template_tiling.cu", q)
+    assert "absinthe_fastwaves_g1" in source and "column kernel" in source
+    assert "kernel absinthe_fastwaves_g1 threads %d" % (32 * (2 + 1)) in descriptor
+    path = tmp_path / "column.cu"
+    path.write_text(source)
+    proc = subprocess.run(nvcc_command(flags, str(path), str(tmp_path / "column.cubin")), capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    sass = subprocess.run(["cuobjdump", "-sass", str(tmp_path / "column.cubin")], capture_output=True, text=True).stdout
+    assert "UTMALDG" in sass and "SHFL" in sass and "BAR.SYNC" in sass
+    assert sass.count("BAR.SYNC") == 1                    # only the start-up barrier: no CTA barrier in the k-loop

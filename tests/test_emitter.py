@@ -105,8 +105,8 @@ def test_per_group_options_override_the_program_wide_ones():
     assert (g1.threads, g1.block, g1.stages) == (384, (1, 1, 2), 2)
     assert (g2.threads, g2.block, g2.stages) == (256, (1, 2, 1), 3)
     text = Plan(P.clone(program)).descriptor_text()
-    assert "group 1 kernel absinthe_group1 threads %d" % (384 + 32) in text
-    assert "group 2 kernel absinthe_group2 threads %d" % (256 + 32) in text
+    assert "group 1 kernel absinthe_fastwaves_g1 threads %d" % (384 + 32) in text
+    assert "group 2 kernel absinthe_fastwaves_g2 threads %d" % (256 + 32) in text
     program["CUDA"]["GROUPS"] = {"1": {"FMAD": True}}
     with pytest.raises(AssertionError, match="not a per-group option"):
         Plan(P.clone(program))

@@ -44,7 +44,7 @@ def test_generate_code_writes_source_and_descriptor(tmp_path):
     G.generate_code("template_tiling.cu", str(tmp_path / "fw.cu"), program)
     source = (tmp_path / "fw.cu").read_text()
     desc = (tmp_path / "fw.desc").read_text()
-    assert "absinthe_group1" in source and "cp.async.bulk.tensor.3d" in source
+    assert "absinthe_fastwaves_g1" in source and "cp.async.bulk.tensor.3d" in source
     assert desc.startswith("absinthe-variant 1\nname fw\n")
     assert "SCHEDULE" in program and [e["TYPE"] for e in program["SCHEDULE"]] == ["PUT", "WAIT", "COMP"]
     with pytest.raises(ValueError):

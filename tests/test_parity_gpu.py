@@ -39,6 +39,13 @@ OPTIONS = [
                                "UNIFORM_WARP": True}),
     ("stream-k", {"STREAM_K": True}),
     ("stream-k-inline", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "PREFETCH": 1}),
+    ("column", {"STREAM_K": "regs"}),
+    ("column-rj2-planes2-halo", {"STREAM_K": "regs", "BLOCK": (2, 1), "COLUMN": {"WARPS": (1, 2), "PLANES": 2},
+                                 "FUSE_HALO": True}),
+    ("column-rj3-planes3", {"STREAM_K": "regs", "BLOCK": (3, 1),
+                            "COLUMN": {"WARPS": (2, 1), "PLANES": 3, "SLOTS": 2, "UNROLL": 1}}),
+    ("column-rj4-branch-halo", {"STREAM_K": "regs", "BLOCK": (4, 1), "COLUMN": {"WARPS": (1, 1)}, "BRANCH": True,
+                                "FUSE_HALO": True, "STORE_CS": True}),
     ("stream-k-shuffle", {"STREAM_K": True, "INLINE": "all", "BLOCK": (3, 1), "SHUFFLE": True, "FUSE_HALO": True,
                           "PREFETCH": 3, "THREADS": 128}),
 ]

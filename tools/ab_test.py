@@ -4,7 +4,8 @@
     ab_test.py [--prebuild] <kernel> '<json options A>' '<json options B>' ...
 
 An option set may hold "_shapes": [[x, y, z], ...] -- tile shapes in points, one per group (or one for all) --
-which replaces the tuned tile counts, and "GROUPS": {"<kernel id>": {...}} for per-group options.  Prints the
+which replaces the tuned tile counts, "_assignment": [group index per stencil] which replaces the tuned fusion
+grouping, and "GROUPS": {"<kernel id>": {...}} for per-group options.  Prints the
 median per variant and per group kernel.  ``--prebuild`` only compiles the candidates (in parallel, no GPU
 needed) so that the variant cache travels to the GPU box with the snapshot.
 """
@@ -23,15 +24,15 @@ def candidate(kernel, extra):
     """The tuned program of ``kernel`` with the option set ``extra`` applied."""
     from absinthe_b200 import programs as P
     cfg = json.load(open(os.path.join(ROOT, "absinthe_b200", "tuned.json")))[kernel]
-    groups = P.split_sequence(P.KERNELS[kernel][1](), cfg["assignment"])
     extra = dict(extra)
+    groups = P.split_sequence(P.KERNELS[kernel][1](), extra.pop("_assignment", cfg["assignment"]))
     tiles = [tuple(t) for t in cfg["tiles"]]
     shapes = extra.pop("_shapes", None)
     if shapes:
         shapes = shapes * len(groups) if len(shapes) == 1 else shapes
         tiles = [tuple(-(-d // s) for d, s in zip(DOMAIN, shape)) for shape in shapes]
     program = P.make_program(kernel, groups, tiles, domain=DOMAIN)
-    program["CUDA"] = dict(cfg["cuda"])
+    program["CUDA"] = {} if extra.pop("_clean", False) else dict(cfg["cuda"])
     program["CUDA"].update(extra)
     return program
 
@@ -47,7 +48,8 @@ def prebuild(job):
 def main():
     args = sys.argv[1:]
     build_only = "--prebuild" in args
-    args = [a for a in args if a != "--prebuild"]
+    check = "--check" in args
+    args = [a for a in args if a not in ("--prebuild", "--check")]
     kernel, overrides = args[0], [json.loads(a) for a in args[1:]]
     if build_only:
         with ProcessPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
@@ -68,6 +70,22 @@ def main():
                 tensors[n] = t
         v.bind([tensors[n] for n in v.inputs], [tensors[n] for n in v.outputs])
         variants.append(v)
+    if check:
+        # every candidate must produce the same bits as the first one (inputs and outputs are shared tensors)
+        want = None
+        for extra, v in zip(overrides, variants):
+            for n in v.outputs:
+                tensors[n].zero_()
+            v.apply()
+            torch.cuda.synchronize()
+            got = {n: tensors[n].clone() for n in v.outputs}
+            if want is None:
+                want = got
+            else:
+                bad = [n for n in want if not torch.equal(want[n], got[n])]
+                print("CHECK %s %s" % ("differs in " + ",".join(bad) if bad else "bit-identical", json.dumps(extra)),
+                      flush=True)
+        del want, got
     samples = [[] for _ in variants]
     per_group = [[[] for _ in range(v.n_groups)] for v in variants]
     for rnd in range(8):
