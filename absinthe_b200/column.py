@@ -36,6 +36,7 @@ FRONT_SLACK = 16
 TAIL_SLACK = 64
 ALIGN_DOUBLES = 16
 MAX_BOX = 256
+SYNC_LINES = 4                   # counter lines per CTA of the wave barrier (work items per CTA it can cover: 4 x grid)
 
 
 def _round_up(value, multiple):
@@ -90,9 +91,12 @@ class ColumnPlan:
         self.launch_threads = self.threads + 32
         self.kc = max(1, int(col.get("PLANES", 1)))
         self.unroll = max(1, int(col.get("UNROLL", max(1, 4 // self.kc))))   # ring slots per unrolled loop trip
-        # ptxas derives the register cap of __launch_bounds__ from the thread count rounded up to 128;
-        # __maxnreg__ gives the kernel every register one resident CTA can have
-        self.maxreg = int(col.get("MAXREG") or min(255, 65536 // self.launch_threads // 8 * 8))
+        # registers are a per-scheduler resource (16384 per SM sub-partition, warps dealt round-robin): the cap
+        # __launch_bounds__ yields is 16384 / (32 * ceil(warps / 4)) -- 255 up to 8 warps, 168 up to 12, 128 up
+        # to 16, producer warp included.  MAXREG (__maxnreg__) only serves to lower it.
+        self.maxreg = col.get("MAXREG")
+        # producers start the n-th work item of every CTA together (see template_column.cu)
+        self.wave_sync = bool(col.get("WAVE_SYNC", True))
         self.fuse_halo = bool(opts["FUSE_HALO"]) and all(s >= 2 * h for s, h in zip(dims, self.H))
         self.acc = {n: A.stencil_accesses(self.by_name[n]["LAMBDA"]) for n in self.names}
         self._schedule()
@@ -242,13 +246,17 @@ class ColumnPlan:
             keys = [k for k in self.uses if k[0] == name]
             amin, amax = min(k[1] for k in keys), max(k[1] for k in keys)
             bmin, bmax = min(k[2] for k in keys), max(k[2] for k in keys)
-            dx = span_x + amax - amin
+            # every lane of every strip reads staged cells, also the lanes left and right of the owning ones
+            # (they evaluate the columns whose results the owning lanes take by shuffle): box column 0 is
+            # column ``amin - first`` of the work item, the last strip ends 32 lanes after its first one
+            dx = span_x - self.useful + 32 + amax - amin
             dx = dx + 1 + (dx + 1) % 2               # even start column + even extent (16-byte TMA rule)
             dy = span_y - self.rj + (bmax - bmin + 1)
             assert dx <= MAX_BOX and dy <= MAX_BOX, "column tile exceeds the TMA box limit"
             cells = dx * dy * self.kc
             self.input_plan.append({
                 "NAME": name, "INDEX": n, "MAP": n, "AMIN": amin, "BMIN": bmin, "DIM": [dx, dy, self.kc],
+                "XLO": amin - self.first,
                 "ROW": dx, "PLANE": dx * dy, "CELLS": cells, "OFFSET": cursor, "QTOP": self.qtop[name],
             })
             cursor += _round_up(cells, ALIGN_DOUBLES)
@@ -278,6 +286,13 @@ class ColumnPlan:
             off += 8
         self.args.append(("tilectl", off, None, None))
         off += 8
+        self.scratch_bytes = 0
+        if self.wave_sync and self.nsub == (1, 1, 1):
+            self.args.append(("scratch", off, None, None))       # wave counters: SYNC_LINES 128-byte lines per CTA
+            off += 8
+            self.scratch_bytes = 128 * SYNC_LINES
+        else:
+            self.wave_sync = False
         self.params_bytes = _round_up(off, 64)
 
     # -- CUDA text --------------------------------------------------------------------------
@@ -306,9 +321,8 @@ class ColumnPlan:
                 _, s, bb, var = op
                 store = ("__stcs(&o_%s[%d * ROW], %s);" if self.opts["STORE_CS"] else "o_%s[%d * ROW] = %s;") % (s, bb, var)
                 if self.fuse_halo:
-                    store += (" if (w.edge || p_%s < HZ || p_%s >= Z - HZ) { const Wrap wr = wrap_of(w.oi + col, "
-                              "w.oj + row0 + %d, p_%s); if (wr.any) store_periodic(o_%s, %d * (long)ROW, wr, %s); }"
-                              % (s, s, bb, s, s, bb, var))
+                    store += (" if (w.edge || p_%s < HZ || p_%s >= Z - HZ) store_wrapped(o_%s, %d * (long)ROW, "
+                              "w.oi + col, w.oj + row0 + %d, p_%s, %s);" % (s, s, s, bb, bb, s, var))
                 lines.append("if (ok_%d && pk_%s) { %s }" % (bb, s, store))
         for dst, src in self.carries:
             lines.append("%s = %s;" % (dst, src))
@@ -318,7 +332,7 @@ class ColumnPlan:
         return {
             "COLUMN": True, "STREAM": False, "ID": self.id, "KERNEL": self.kernel_name,
             "THREADS": self.threads, "WARPS": self.warps, "LAUNCH_THREADS": self.launch_threads,
-            "WX": self.wx, "WY": self.wy, "RJ": self.rj, "KC": self.kc, "UNROLL": self.unroll, "MAXREG": self.maxreg, "NS": self.ns, "STAGES": self.ns,
+            "WX": self.wx, "WY": self.wy, "RJ": self.rj, "KC": self.kc, "WAVE_SYNC": self.wave_sync, "SYNC_LINES": SYNC_LINES, "UNROLL": self.unroll, "MAXREG": self.maxreg, "NS": self.ns, "STAGES": self.ns,
             "FIRST": self.first, "LAST": self.last, "USEFUL": self.useful, "KMIN": self.kmin,
             "T": self.T, "O": self.O, "N": self.N, "B": self.B, "NSUB": self.nsub,
             "NSUB_TOTAL": self.nsub[0] * self.nsub[1], "TILES": self.tiles, "TMA": True,
@@ -344,6 +358,7 @@ class ColumnPlan:
         """
         planes = planes or (4 - self.kmin)
         poison = None
+        boxes = {p["NAME"]: p for p in self.input_plan}
         state = {name: [poison] * 32 for name in self.carried}
         checked = 0
         for step in range(planes - self.kmin):
@@ -351,7 +366,13 @@ class ColumnPlan:
             for op in self.ops:
                 if op[0] == "load":
                     _, var, f, a, bb = op
-                    state[var] = [(f, lane - self.first + a, bb, kk + self.qtop[f]) for lane in range(32)]
+                    p = boxes[f]
+                    # staged cell of the last strip / last warp row, worst-case parity: must be inside the box
+                    inside = [0 <= lane + a - p["AMIN"] and (self.wx - 1) * self.useful + lane + a - p["AMIN"] + 1
+                              < p["DIM"][0] and 0 <= bb - p["BMIN"] and (self.wy - 1) * self.rj + bb - p["BMIN"]
+                              < p["DIM"][1] for lane in range(32)]
+                    state[var] = [(f, lane - self.first + a, bb, kk + self.qtop[f]) if inside[lane] else poison
+                                  for lane in range(32)]
                 elif op[0] == "shfl":
                     _, var, src, a = op
                     state[var] = [state[src][lane + a] if 0 <= lane + a < 32 else poison for lane in range(32)]

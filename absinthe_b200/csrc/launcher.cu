@@ -546,23 +546,27 @@ int absinthe_variant_load(const char* descriptor, const void* cubin, size_t cubi
     cudaError_t e = cudaGetDeviceProperties(&prop, device);
     if (e != cudaSuccess) { delete v; return fail((int)e, "cudaGetDeviceProperties: %s", cudaGetErrorString(e)); }
     v->sms = prop.multiProcessorCount;
+    // failure paths: format the message while the variant (and the strings it owns) is alive, then free it
+    auto give_up = [&](int code) { absinthe_variant_free(v); return code; };
     CUresult r = g_drv.ModuleLoadData(&v->module, cubin);
-    if (r != CUDA_SUCCESS) { delete v; return fail((int)r, "cuModuleLoadData failed: %s (is the cubin built for sm_%d%d?)", drv_error(r), prop.major, prop.minor); }
+    if (r != CUDA_SUCCESS) return give_up(fail((int)r, "cuModuleLoadData failed: %s (is the cubin built for sm_%d%d?)", drv_error(r), prop.major, prop.minor));
     for (Group& g : v->groups) {
         r = g_drv.ModuleGetFunction(&g.fn, v->module, g.symbol.c_str());
-        if (r != CUDA_SUCCESS) { absinthe_variant_free(v); return fail((int)r, "kernel %s not found: %s", g.symbol.c_str(), drv_error(r)); }
+        if (r != CUDA_SUCCESS) return give_up(fail((int)r, "kernel %s not found: %s", g.symbol.c_str(), drv_error(r)));
         if (g.smem > 48 * 1024) {
             r = g_drv.FuncSetAttribute(g.fn, CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)g.smem);
-            if (r != CUDA_SUCCESS) { absinthe_variant_free(v); return fail((int)r, "kernel %s: %zu bytes of shared memory refused: %s", g.symbol.c_str(), g.smem, drv_error(r)); }
+            if (r != CUDA_SUCCESS) return give_up(fail((int)r, "kernel %s: %zu bytes of shared memory refused: %s", g.symbol.c_str(), g.smem, drv_error(r)));
         }
         int blocks = 0;
         r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&blocks, g.fn, g.threads, g.smem);
-        if (r != CUDA_SUCCESS || blocks < 1) { absinthe_variant_free(v); return fail((int)r, "kernel %s cannot be resident (threads %d, smem %zu)", g.symbol.c_str(), g.threads, g.smem); }
+        if (r != CUDA_SUCCESS || blocks < 1) return give_up(fail(r != CUDA_SUCCESS ? (int)r : -4, "kernel %s cannot be resident (threads %d, smem %zu)", g.symbol.c_str(), g.threads, g.smem));
         g.blocks_per_sm = blocks;
         if (g.scratch_bytes) {
             size_t total = g.scratch_bytes * (size_t)grid_for(v, g, g.tiles);
             e = cudaMalloc(&g.scratch, total);
-            if (e != cudaSuccess) { absinthe_variant_free(v); return fail((int)e, "scratch allocation of %zu bytes failed", total); }
+            if (e != cudaSuccess) { g.scratch = nullptr; return give_up(fail((int)e, "scratch allocation of %zu bytes failed", total)); }
+            e = cudaMemset(g.scratch, 0, total);
+            if (e != cudaSuccess) return give_up(fail((int)e, "scratch of kernel %s: cudaMemset failed: %s", g.symbol.c_str(), cudaGetErrorString(e)));
         }
     }
     // inter-group temporaries are owned by the library (zero-initialised like sarray_3d(0.0))
@@ -570,9 +574,10 @@ int absinthe_variant_load(const char* descriptor, const void* cubin, size_t cubi
         if (f.kind == kTemp) {
             size_t bytes = (size_t)v->geo.cells() * 8;
             e = cudaMalloc(&f.ptr, bytes);
-            if (e != cudaSuccess) { absinthe_variant_free(v); return fail((int)e, "temporary '%s': %zu bytes refused", f.name.c_str(), bytes); }
-            cudaMemset(f.ptr, 0, bytes);
+            if (e != cudaSuccess) { f.ptr = nullptr; return give_up(fail((int)e, "temporary '%s': %zu bytes refused", f.name.c_str(), bytes)); }
             f.owned = true;
+            e = cudaMemset(f.ptr, 0, bytes);
+            if (e != cudaSuccess) return give_up(fail((int)e, "temporary '%s': cudaMemset failed: %s", f.name.c_str(), cudaGetErrorString(e)));
         }
     *out = v;
     return 0;

@@ -692,14 +692,17 @@ class Plan:
             lines.append("field %s tmp" % name)
         for g in self.groups:
             lines.append("group %d kernel %s threads %d smem %d tiles %d params %d "
-                         "training_step %d fused_halo %d" % (
+                         "training_step %d fused_halo %d%s" % (
                              g.id, g.kernel_name, g.launch_threads, g.smem_bytes, g.tiles, g.params_bytes,
-                             training.get("STRIDE", 20), int(g.fuse_halo)))
+                             training.get("STRIDE", 20), int(g.fuse_halo),
+                             " scratch %d" % g.scratch_bytes if getattr(g, "scratch_bytes", 0) else ""))
             for kind, off, name, dim in g.args:
                 if kind == "tmap":
                     lines.append("arg tmap %d %s %d %d %d" % (off, name, dim[0], dim[1], dim[2]))
                 elif kind == "ptr":
                     lines.append("arg ptr %d %s" % (off, name))
+                elif kind == "scratch":
+                    lines.append("arg scratch %d" % off)
                 else:
                     lines.append("arg tilectl %d" % off)
             for name in g.outputs:

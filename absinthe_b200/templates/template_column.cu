@@ -25,8 +25,26 @@ extern "C" __global__ void {% if g.MAXREG %}__maxnreg__({{g.MAXREG}}){% else %}_
     __syncthreads();
     if (warp >= {{g.WARPS}}) {
         if (lane == 0) {
+{%- if g.WAVE_SYNC %}
+            // The producers of all CTAs start their n-th work item together (a grid-wide arrive/wait per item, on a
+            // counter line of its own; the consumers keep draining the ring meanwhile).  Work items n of the grid are
+            // neighbouring tiles: started together they stay within a few planes of each other over one column, so
+            // the halo cells two tiles share are requested within the L2's reach of each other and only one of the
+            // requests goes to HBM.  Left to drift (persistent CTAs, no synchronisation) none of them did (ncu:
+            // dram reads = requested box bytes, 1.55x the fields).  Waiting is bounded; the last CTA to leave resets.
+            int* const sync = prm.progress;
+            const int lines = (int)gridDim.x * {{g.SYNC_LINES}} - 1;        // last line: departures
+            const bool synced = prm.tile_step == 1 && gridDim.x > 1;
+{%- endif %}
             int chunk = 0;
             for (int n = 0; n < my_work; ++n) {
+{%- if g.WAVE_SYNC %}
+                if (synced && n > 0 && n < lines) {
+                    const int want = min((int)gridDim.x, prm.tile_count - n * (int)gridDim.x);
+                    atomicAdd(sync + n * 32, 1);
+                    for (int spin = 0; spin < 50000 && peek(sync + n * 32) < want; ++spin) __nanosleep(200);
+                }
+{%- endif %}
                 const WorkItem w = locate{{g.ID}}(n, prm.tile_step);
                 if (!w.live) continue;
                 const int kb = w.ok + w.bk, ke = w.ok + w.ek;
@@ -37,10 +55,15 @@ extern "C" __global__ void {% if g.MAXREG %}__maxnreg__({{g.MAXREG}}){% else %}_
                     double* const dst = smem + slot * {{g.SLOT_DOUBLES}};
                     mbar_expect_tx(&full[slot], {{g.SLOT_BYTES}});
 {%- for f in g.INPUTS %}
-                    tma_load_box(dst + {{f.OFFSET}}, &prm.map[{{f.MAP}}], &full[slot], (HX + w.oi + ({{f.AMIN}})) & ~1, HY + w.oj + ({{f.BMIN}}), HZ + kb + ({{g.KMIN + f.QTOP}}) + c * {{g.KC}});
+                    tma_load_box(dst + {{f.OFFSET}}, &prm.map[{{f.MAP}}], &full[slot], (HX + w.oi + ({{f.XLO}})) & ~1, HY + w.oj + ({{f.BMIN}}), HZ + kb + ({{g.KMIN + f.QTOP}}) + c * {{g.KC}});
 {%- endfor %}
                 }
             }
+{%- if g.WAVE_SYNC %}
+            if (synced && atomicAdd(sync + lines * 32, 1) == (int)gridDim.x - 1) {
+                for (int n = 0; n <= lines; ++n) post(sync + n * 32, 0);      // clean counters for the next launch
+            }
+{%- endif %}
         }
         return;
     }
@@ -60,7 +83,7 @@ extern "C" __global__ void {% if g.MAXREG %}__maxnreg__({{g.MAXREG}}){% else %}_
         const bool ok_{{b}} = okc && row0 + {{b}} >= w.bj && row0 + {{b}} < w.ej;
 {%- endfor %}
 {%- for f in g.INPUTS %}
-        const int off_{{f.NAME}} = {{f.OFFSET}} + row0 * {{f.ROW}} + col + ((HX + w.oi + ({{f.AMIN}})) & 1);
+        const int off_{{f.NAME}} = {{f.OFFSET}} + row0 * {{f.ROW}} + sx * {{g.USEFUL}} + lane + ((HX + w.oi + ({{f.XLO}})) & 1);
 {%- endfor %}
         const long origin = (HX + w.oi + col) + (long)(HY + w.oj + row0) * ROW + (long)HZ * PLANE;
 {%- for o in g.OUT_LEADS %}

@@ -61,6 +61,7 @@ def main():
     variants, tensors = [], {}
     gen = torch.Generator(device="cuda").manual_seed(7)
     for extra in overrides:
+        print("loading", json.dumps(extra), flush=True)
         v = Variant.from_program(candidate(kernel, extra))
         dims = (v.X, v.Y, v.Z, v.HX, v.HY, v.HZ)
         for n in v.inputs + v.outputs:
