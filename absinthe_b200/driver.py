@@ -12,9 +12,10 @@ reference's (ref diffusion.py:298-360, fitcache.py:88-187):
     -p / --parse F    <folder>/F (stdout of run.sh) -> results.csv / auto.csv
     -f / --folder D   working directory
 
-``-o`` and ``-e`` evaluate the reference's MILP model; they import ``stencil_optimizer`` from a
-reference checkout (``ABSINTHE_REFERENCE`` or ``/root/reference``) and solve it with the ``cplex``
-shim of ``tools/cplex`` -- that component is control plane and deliberately not rebuilt here.
+``-o`` and ``-e`` evaluate the analytical model (``optimizer.py``: the reference's MILP, built in process and
+solved with HiGHS; ``ABSINTHE_SOLVER=cplex`` shells out to a ``cplex`` like the reference).  An exploration
+solves ~175 independent MILPs; they run in a process pool (``ABSINTHE_WORKERS``), each bounded by
+``ABSINTHE_MILP_SECONDS``; ``ABSINTHE_SEED`` makes the random sample of groupings reproducible.
 """
 
 import csv
@@ -58,44 +59,189 @@ def auto_tune(kernel, experiments, domain=None, counts_xy=AUTO_COUNTS_XY, counts
                                                        variant=name, outputs=outputs[idx], RUNS=16)
 
 
-def _reference_optimizer():
-    root = os.environ.get("ABSINTHE_REFERENCE", "/root/reference")
-    if not os.path.isfile(os.path.join(root, "stencil_optimizer.py")):
-        raise SystemExit("-o/-e need the reference's stencil_optimizer.py (set ABSINTHE_REFERENCE) and the "
-                         "cplex shim of tools/ on PATH")
-    shim = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
-    os.environ["PATH"] = shim + os.pathsep + os.environ.get("PATH", "")
-    sys.path.insert(0, root)
-    try:
-        import stencil_optimizer
-    finally:
-        sys.path.remove(root)
-    return stencil_optimizer.optimize_program
+# HAND / AUTO of the reference drivers as (group index per stencil, tile counts per group)
+# (ref diffusion.py:157-189, advection.py:145-177, fastwaves.py:138-183)
+SPECIAL = {
+    "diffusion": {"HAND": ([0] * 16, [(1, 1, 60)]), "AUTO": ([n // 4 for n in range(16)], [(1, 1, 60)] * 4)},
+    "advection": {"HAND": ([0] * 8, [(1, 1, 60)]), "AUTO": ([0] * 8, [(1, 1, 30)])},
+    "fastwaves": {"HAND": ([0] * 6 + [1] * 3, [(1, 8, 8)] * 2), "AUTO": ([0] * 6 + [1] * 3, [(1, 4, 5), (1, 2, 5)])},
+}
+MAX_GROUPS = 5          # groupings with a group index above 4 are not explored (ref diffusion.py:221)
+SAMPLES = 20            # random groupings per exploration (ref diffusion.py:223)
 
 
-def search_optimum(kernel, experiments, folder):
+def model_program(kernel, variant, groups=None, tiling=None, name=None, domain=None):
+    """A driver-level program ready for ``optimize_program``: sequence fixed, optional CONSTRAINTS."""
     program = P.base_program(kernel)
     program["STENCILS"] = P.KERNELS[kernel][0]()
     program["SEQUENCE"] = P.KERNELS[kernel][1]()
-    _reference_optimizer()(folder + program["NAME"], program)
+    program["VARIANT"] = variant
+    if name:
+        program["NAME"] = name
+    if domain:
+        program["X"], program["Y"], program["Z"] = domain
+    if groups is not None:
+        program["CONSTRAINTS"]["GROUPS"] = list(groups)
+    if tiling is not None:
+        program["CONSTRAINTS"]["TILING"] = list(tiling)
+    return program
+
+
+def fixed_tile_counts(program, stencils, counts):
+    """CONSTRAINTS.TILING entries that pin the tile counts of ``stencils`` to ``counts``: ``(dim, s, -(c+1))``
+    is n <= c and ``(dim, s, c-1)`` is n >= c (ref stencil_optimizer.py:587-594); bounds the model has anyway
+    (1 <= n <= extent) are not repeated, like in the reference's HAND / AUTO lists."""
+    out = []
+    for stencil in stencils:
+        for dim, count in zip("xyz", counts):
+            if count < program[dim.upper()]:
+                out.append((dim, stencil, -(count + 1)))
+            if count > 1:
+                out.append((dim, stencil, count - 1))
+    return out
+
+
+def special_program(kernel, variant, domain=None):
+    """HAND / AUTO: groups and tile counts given, capacity and slack constraints lifted (ref diffusion.py:169-172);
+    CORES is lowered to the tile count where the pinned tiling has fewer tiles than the machine has SMs."""
+    assignment, tiles = SPECIAL[kernel][variant]
+    sequence = P.KERNELS[kernel][1]()
+    program = model_program(kernel, variant, groups=list(zip(sequence, assignment)), domain=domain)
+    tiling = []
+    for index, names in enumerate(P.split_sequence(sequence, assignment)):
+        tiling += fixed_tile_counts(program, names, tiles[index])
+    program["CONSTRAINTS"]["TILING"] = tiling
+    program["MACHINE"]["CAPACITY"] = 2 ** 31
+    program["MACHINE"]["CORES"] = min([program["MACHINE"]["CORES"]] + [t[0] * t[1] * t[2] for t in tiles])
+    program["SLACK"] = {"SIZE": 1.0, "CORES": 1.0}
+    return program
+
+
+def enumerate_groupings(sequence, limit=MAX_GROUPS):
+    """Every assignment of consecutive stencils to groups 0, 1, ... with at most ``limit`` groups."""
+    out = [[0]]
+    for _ in sequence[1:]:
+        out = [g + [g[-1] + step] for g in out for step in (0, 1) if g[-1] + step < limit]
+    return out
+
+
+def grouping_of(kernel, variant):
+    """Group indexes encoded in a variant name ``<kernel>-g0-g1-...[-m|p{x,y,z}]`` and its suffix (or None)."""
+    sequence = P.KERNELS[kernel][1]()
+    parts = variant.split("-")
+    digits = [int(t) for t in parts[1:1 + len(sequence)]]
+    suffix = parts[1 + len(sequence)] if len(parts) > 1 + len(sequence) else None
+    return digits, suffix
+
+
+def neighbour_tiling(program, solved, suffix):
+    """The tile-count neighbours of a solved grouping (ref diffusion.py:240-274): ``-m<dim>`` allows at most
+    N - 1 tiles along ``dim`` in every group that has more than one, ``-p<dim>`` demands at least N + 1 in every
+    group that has fewer tiles than points, N being the group's tile count in the solution."""
+    dim, key = suffix[1], "N" + suffix[1].upper()
+    out = []
+    for outer in solved["TILING"]["GROUPS"]:
+        info = outer["GROUPS"][0]
+        if suffix[0] == "m" and info[key] > 1:
+            out += [(dim, s, -info[key]) for s in info["STENCILS"]]
+        if suffix[0] == "p" and info[key] < program[dim.upper()]:
+            out += [(dim, s, info[key]) for s in info["STENCILS"]]
+    return out
+
+
+def _solve(job):
+    """One MILP in a worker process: (key, folder, program) -> (key, program) with TILING / OBJECTIVE."""
+    import contextlib
+    import io
+    from .optimizer import optimize_program
+    key, folder, program = job
+    log = io.StringIO()
+    try:
+        with contextlib.redirect_stdout(log):
+            optimize_program(folder + key, program)
+    except Exception as exc:                      # an infeasible neighbour is dropped, like a failed cplex run
+        program["ERROR"] = str(exc)[:200]
+    return key, program
+
+
+def solve_all(jobs, workers=None):
+    """Solve independent programs in parallel (HiGHS is single threaded; an exploration holds ~175 of them)."""
+    from concurrent.futures import ProcessPoolExecutor
+    workers = workers or int(os.environ.get("ABSINTHE_WORKERS", os.cpu_count() or 1))
+    if workers <= 1 or len(jobs) <= 1:
+        return [_solve(job) for job in jobs]
+    with ProcessPoolExecutor(max_workers=workers) as pool:
+        return list(pool.map(_solve, jobs))
+
+
+def search_optimum(kernel, experiments, folder, domain=None):
+    from .optimizer import optimize_program
+    program = model_program(kernel, kernel, domain=domain)
+    optimize_program(folder + program["NAME"], program)
     experiments[program["NAME"]] = program
 
 
-def explore_space(kernel, experiments, folder):
-    """OPT, MAX and MIN of the model (the reference's exploration needs the same solver)."""
-    optimize = _reference_optimizer()
+def explore_space(kernel, experiments, folder, domain=None, groupings=None, samples=SAMPLES, seed=None, suffixes=None):
+    """OPT / HAND / AUTO / MAX / MIN, then ``samples`` random groupings (plus the five special ones), each with its
+    six tile-count neighbours, deduplicated by TILING (ref diffusion.py:137-283).
+
+    ``groupings`` replaces the random sample by given group-index lists (``grouping_of`` extracts them from the
+    variant names the reference ships, whose own sample was unseeded); ``seed`` makes the sample reproducible;
+    ``suffixes`` restricts the neighbours (default: all of mx my mz px py pz)."""
+    import random
     sequence = P.KERNELS[kernel][1]()
-    constraints = {"OPT": None, "MAX": [(s, 0) for s in sequence],
-                   "MIN": [(s, n) for n, s in enumerate(sequence)]}
-    for name, groups in constraints.items():
-        program = P.base_program(kernel)
-        program["STENCILS"] = P.KERNELS[kernel][0]()
-        program["SEQUENCE"] = sequence
-        program["VARIANT"] = name
-        if groups is not None:
-            program["CONSTRAINTS"]["GROUPS"] = groups
-        optimize(folder + name, program)
-        experiments[name] = program
+    special = {
+        "OPT": model_program(kernel, "OPT", domain=domain),
+        "HAND": special_program(kernel, "HAND", domain),
+        "AUTO": special_program(kernel, "AUTO", domain),
+        "MAX": model_program(kernel, "MAX", groups=[(s, 0) for s in sequence], domain=domain),
+        "MIN": model_program(kernel, "MIN", groups=[(s, n) for n, s in enumerate(sequence)], domain=domain),
+    }
+    for key, program in solve_all([(key, folder, program) for key, program in special.items()]):
+        if "TILING" in program:
+            experiments[key] = program
+    # the optimum's own grouping becomes a constraint of the exploration (ref :151-155)
+    if "OPT" in experiments:
+        experiments["OPT"]["CONSTRAINTS"]["GROUPS"] = [
+            (s, index) for index, outer in enumerate(experiments["OPT"]["TILING"]["GROUPS"])
+            for s in outer["GROUPS"][0]["STENCILS"]]
+    if groupings is None:
+        rng = random.Random(seed if seed is not None else os.environ.get("ABSINTHE_SEED"))
+        candidates = enumerate_groupings(sequence)
+        groupings = rng.sample(candidates, min(samples, len(candidates)))
+    groupings = [list(g) for g in groupings]
+    for program in experiments.values():
+        digits = [index for _, index in program["CONSTRAINTS"]["GROUPS"]]
+        if digits not in groupings:
+            groupings.append(digits)
+    base = {}
+    for digits in groupings:
+        key = "%s-%s" % (kernel, "-".join(str(d) for d in digits))
+        base[key] = model_program(kernel, key, groups=list(zip(sequence, digits)), name=key, domain=domain)
+    exploration = {}
+    for key, program in solve_all([(key, folder, program) for key, program in base.items()]):
+        if "TILING" in program:
+            exploration[key] = program
+    jobs = []
+    for key, solved in exploration.items():
+        for suffix in suffixes if suffixes is not None else ("mx", "my", "mz", "px", "py", "pz"):
+            name = "%s-%s" % (key, suffix)
+            jobs.append((name, folder, model_program(
+                kernel, name, groups=solved["CONSTRAINTS"]["GROUPS"], name=name, domain=domain,
+                tiling=neighbour_tiling(solved, solved, suffix))))
+    for key, program in solve_all(jobs):
+        if "TILING" in program:
+            exploration[key] = program
+    for key, program in exploration.items():          # remove duplicates (ref :276-283)
+        if any(existing["TILING"] == program["TILING"] for existing in experiments.values()):
+            print("-> found existing experiment " + key)
+        else:
+            experiments[key] = program
+    store_objectives(experiments, folder)
+
+
+def store_objectives(experiments, folder):
+    """``estimates.csv``: VAR, EST (ref diffusion.py:286-295)."""
     with open(folder + "estimates.csv", "w") as handle:
         out = csv.writer(handle, delimiter=",", quotechar="'", lineterminator="\n")
         out.writerow(["VAR", "EST"])

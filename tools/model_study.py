@@ -2,8 +2,7 @@
 """Model-vs-measurement study: does the analytical model, re-parameterised
 for the B200, rank implementation variants like the GPU does?
 
-  plan    (development container: needs the reference's stencil_optimizer.py + tools/cplex)
-          solve the MILP for a spread of fusion groupings -> variants JSON (tiling + estimate)
+  plan    solve the MILP (absinthe_b200/optimizer.py, HiGHS, in parallel) for a spread of fusion groupings -> variants JSON (tiling + estimate)
   measure (GPU box) time every variant of a variants JSON -> Spearman(estimate, measured)
 """
 import argparse
@@ -19,8 +18,7 @@ sys.path.insert(0, ROOT)
 
 def plan(args):
     from absinthe_b200 import programs as P
-    from absinthe_b200.driver import _reference_optimizer
-    optimize = _reference_optimizer()
+    from absinthe_b200.driver import model_program, solve_all
     domain = tuple(int(v) for v in args.domain.split("x"))
     seq = P.KERNELS[args.kernel][1]()
     rng = random.Random(args.seed)
@@ -32,21 +30,15 @@ def plan(args):
         if a not in assignments:
             assignments.append(a)
     os.makedirs(args.work, exist_ok=True)
-    variants = []
+    jobs = []
     for n, a in enumerate(assignments):
-        program = P.base_program(args.kernel)
-        program["X"], program["Y"], program["Z"] = domain
-        program["STENCILS"] = P.KERNELS[args.kernel][0]()
-        program["SEQUENCE"] = seq
-        program["VARIANT"] = "%s-%s" % (args.kernel, "-".join(map(str, a)))
-        program["CONSTRAINTS"]["GROUPS"] = list(zip(seq, a))
-        try:
-            optimize(os.path.join(args.work, "v%d" % n), program)
-        except (SystemExit, Exception) as exc:
-            print("skip", a, exc)
-            continue
+        name = "%s-%s" % (args.kernel, "-".join(map(str, a)))
+        jobs.append(("v%d" % n, os.path.join(args.work, ""), model_program(args.kernel, name, groups=list(zip(seq, a)),
+                                                                         domain=domain)))
+    variants = []
+    for (key, program), a in zip(solve_all(jobs), assignments):
         if "TILING" not in program or "OBJECTIVE" not in program:
-            print("skip (no incumbent within the time limit)", a)
+            print("skip (no incumbent within the time limit)", a, program.get("ERROR", ""))
             continue
         tiles = [[g["GROUPS"][0][k] for k in ("NX", "NY", "NZ")] for g in program["TILING"]["GROUPS"]]
         variants.append({"assignment": a, "tiles": tiles, "estimate": float(program["OBJECTIVE"])})
