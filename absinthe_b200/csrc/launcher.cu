@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -75,8 +76,7 @@ int resolve(const char* name, F& slot) {
     return 0;
 }
 
-int driver() {
-    if (g_drv.ready) return 0;
+int driver_resolve_all() {
     int rc = 0;
     if ((rc = resolve("cuModuleLoadData", g_drv.ModuleLoadData))) return rc;
     if ((rc = resolve("cuModuleUnload", g_drv.ModuleUnload))) return rc;
@@ -87,8 +87,22 @@ int driver() {
     if ((rc = resolve("cuLaunchKernel", g_drv.LaunchKernel))) return rc;
     if ((rc = resolve("cuTensorMapEncodeTiled", g_drv.TensorMapEncodeTiled))) return rc;
     if ((rc = resolve("cuGetErrorString", g_drv.GetErrorString))) return rc;
-    g_drv.ready = true;
     return 0;
+}
+
+// several host threads may load their first variant at the same time (one per device): the table is
+// resolved exactly once; a failure is remembered and reported to every caller
+int driver() {
+    static std::once_flag once;
+    static int status = 0;
+    static std::string message;
+    std::call_once(once, [] {
+        status = driver_resolve_all();
+        if (status) message = g_error;
+        g_drv.ready = status == 0;
+    });
+    if (status) g_error = message;
+    return status;
 }
 
 const char* drv_error(CUresult r) {
@@ -239,9 +253,23 @@ __global__ void faces_kernel(FieldList fields, double* low, double* high, Geomet
     }
 }
 
+constexpr int kMaxDevices = 64;
+
+// multiprocessors of the current device (queried once per device)
+int sm_count() {
+    static int cached[kMaxDevices] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 132;
+    if (!cached[dev]) {
+        int n = 0;
+        cached[dev] = cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0 ? n : 132;
+    }
+    return cached[dev];
+}
+
 int launch_grid(long items, int threads) {
     long blocks = (items + threads - 1) / threads;
-    return (int)std::max(1L, std::min(blocks, 148L * 16));
+    return (int)std::max(1L, std::min(blocks, (long)sm_count() * 16));
 }
 
 int periodic_update(const FieldList& fields, const Geometry& g, int mask, cudaStream_t stream) {
@@ -346,8 +374,36 @@ struct absinthe_variant {
 
 namespace {
 
-double* g_flush = nullptr;
-const long kFlushDoubles = 48L * 1024 * 1024;  // 384 MB > 2 x L2
+std::mutex g_device_mutex;                       // guards the per-device scratch below
+double* g_flush[kMaxDevices] = {};               // one flush buffer per device
+unsigned long long* g_counters[kMaxDevices] = {};   // error / match counters of absinthe_compare_fields
+const long kFlushDoubles = 48L * 1024 * 1024;    // 384 MB > 2 x L2
+
+// scratch of the current device, allocated on first use
+template <typename T>
+int device_scratch(T* (&table)[kMaxDevices], size_t bytes, T** out) {
+    int dev = 0;
+    RT(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return fail(-3, "device %d out of range", dev);
+    std::lock_guard<std::mutex> lock(g_device_mutex);
+    if (!table[dev]) RT(cudaMalloc(&table[dev], bytes));
+    *out = table[dev];
+    return 0;
+}
+
+// every entry point that launches runs on the variant's device, whatever device the caller left current
+struct OnDevice {
+    int previous = -1;
+    bool ok = true;
+    explicit OnDevice(int device) {
+        if (cudaGetDevice(&previous) != cudaSuccess) previous = -1;
+        if (previous != device) ok = cudaSetDevice(device) == cudaSuccess;
+    }
+    ~OnDevice() {
+        int now = -1;
+        if (previous >= 0 && cudaGetDevice(&now) == cudaSuccess && now != previous) cudaSetDevice(previous);
+    }
+};
 
 int find_field(const absinthe_variant* v, const std::string& name) {
     for (size_t n = 0; n < v->fields.size(); ++n)
@@ -650,7 +706,8 @@ int absinthe_variant_fused_halo(const absinthe_variant* v) {
 
 int absinthe_variant_bind(absinthe_variant* v, const double* const* d_inputs, double* const* d_outputs) {
     if (!v) return fail(-3, "null variant");
-    RT(cudaSetDevice(v->device));
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     for (size_t n = 0; n < v->inputs.size(); ++n) {
         if (!d_inputs || !d_inputs[n]) return fail(-3, "input %zu is null", n);
         v->fields[v->inputs[n]].ptr = const_cast<double*>(d_inputs[n]);
@@ -671,6 +728,8 @@ int absinthe_variant_bind(absinthe_variant* v, const double* const* d_inputs, do
 int absinthe_variant_apply(absinthe_variant* v, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     cudaStream_t s = (cudaStream_t)stream;
     for (Group& g : v->groups) {
         if ((rc = launch_group(v, g, false, s))) return rc;
@@ -682,6 +741,8 @@ int absinthe_variant_apply(absinthe_variant* v, void* stream) {
 int absinthe_variant_apply_graph(absinthe_variant* v, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     cudaStream_t s = (cudaStream_t)stream;
     if (!v->graph) {
         // capture on a private stream (the legacy default stream cannot be captured); the
@@ -704,6 +765,8 @@ int absinthe_variant_apply_graph(absinthe_variant* v, void* stream) {
 int absinthe_variant_apply_group(absinthe_variant* v, int group, int with_halo, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     for (Group& g : v->groups)
         if (g.id == group) {
             if ((rc = launch_group(v, g, false, (cudaStream_t)stream))) return rc;
@@ -715,6 +778,8 @@ int absinthe_variant_apply_group(absinthe_variant* v, int group, int with_halo, 
 int absinthe_variant_halo_group(absinthe_variant* v, int group, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     for (Group& g : v->groups)
         if (g.id == group) return halo_group(v, g, (cudaStream_t)stream);
     return fail(-3, "variant '%s' has no group %d", v->name.c_str(), group);
@@ -724,6 +789,8 @@ static int group_faces(absinthe_variant* v, int group, double* low, double* high
                        void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     for (Group& g : v->groups)
         if (g.id == group) {
             if (g.halo_fields.empty()) return 0;
@@ -776,8 +843,10 @@ double* absinthe_variant_field_ptr(const absinthe_variant* v, const char* name) 
 }
 
 int absinthe_flush_l2(void* stream) {
-    if (!g_flush) RT(cudaMalloc(&g_flush, kFlushDoubles * 8));
-    flush_kernel<<<148 * 8, 256, 0, (cudaStream_t)stream>>>(g_flush, kFlushDoubles, 0.0);
+    double* buffer = nullptr;
+    int rc = device_scratch(g_flush, kFlushDoubles * 8, &buffer);
+    if (rc) return rc;
+    flush_kernel<<<sm_count() * 8, 256, 0, (cudaStream_t)stream>>>(buffer, kFlushDoubles, 0.0);
     RT(cudaGetLastError());
     return 0;
 }
@@ -786,9 +855,10 @@ int absinthe_variant_run(absinthe_variant* v, void* stream, int runs, int flush,
                          float* total_ms, float* halo_ms) {
     int rc = require_bound(v);
     if (rc) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     if (runs <= 0 || !total_ms || !halo_ms) return fail(-3, "absinthe_variant_run: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
-    RT(cudaSetDevice(v->device));
     const size_t need = 1 + 2 * v->groups.size();
     while (v->events.size() < need) {
         cudaEvent_t e;
@@ -869,6 +939,8 @@ int absinthe_variant_host_interior(absinthe_variant* v, int enable) {
 
 int absinthe_variant_wait_host(absinthe_variant* v) {
     if (!v) return fail(-3, "null variant");
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     if (v->host_waited < v->host_issued) {
         RT(cudaEventSynchronize(v->ev_out[v->host_waited % kHostDepth]));
         ++v->host_waited;
@@ -880,6 +952,8 @@ int absinthe_variant_apply_host(absinthe_variant* v, const double* const* h_inpu
                                 double* const* h_outputs, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     while (v->host_waited < v->host_issued)   // async steps still in flight use the same device fields
         if ((rc = absinthe_variant_wait_host(v))) return rc;
     cudaStream_t s = (cudaStream_t)stream;
@@ -896,8 +970,26 @@ int absinthe_variant_apply_host_async(absinthe_variant* v, const double* const* 
                                       double* const* h_outputs, void* stream) {
     int rc = require_bound(v);
     if (rc) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d of variant '%s'", v->device, v->name.c_str());
     if (v->host_issued - v->host_waited >= kHostDepth)
         return fail(-6, "%d host steps already in flight: call absinthe_variant_wait_host first", kHostDepth);
+    // the copies of this path overlap with the caller and with each other only from page-locked memory; a
+    // pageable pointer would silently serialise them (and the call would return before the data is safe)
+    for (size_t n = 0; n < v->inputs.size() + v->outputs.size(); ++n) {
+        const void* p = n < v->inputs.size() ? (const void*)h_inputs[n] : (const void*)h_outputs[n - v->inputs.size()];
+        if (!p) {
+            if (n < v->inputs.size()) continue;          // a null input keeps the device-resident field
+            return fail(-3, "host output %zu is null", n - v->inputs.size());
+        }
+        cudaPointerAttributes attr{};
+        cudaError_t pe = cudaPointerGetAttributes(&attr, p);
+        if (pe != cudaSuccess) { cudaGetLastError(); return fail((int)pe, "cudaPointerGetAttributes: %s", cudaGetErrorString(pe)); }
+        if (attr.type != cudaMemoryTypeHost)
+            return fail(-7, "absinthe_variant_apply_host_async needs page-locked host buffers (%s %zu is %s memory)",
+                        n < v->inputs.size() ? "input" : "output", n < v->inputs.size() ? n : n - v->inputs.size(),
+                        attr.type == cudaMemoryTypeUnregistered ? "pageable" : "device");
+    }
     cudaStream_t s = (cudaStream_t)stream;
     if (!v->h2d_stream) {
         RT(cudaStreamCreateWithFlags(&v->h2d_stream, cudaStreamNonBlocking));
@@ -978,7 +1070,8 @@ int absinthe_compare_fields(const double* d_expected, const double* d_actual, in
     if (!d_expected || !d_actual || !errors || !matches) return fail(-3, "absinthe_compare_fields: null argument");
     Geometry g{X, Y, Z, HX, HY, HZ};
     unsigned long long* counters = nullptr;
-    RT(cudaMalloc(&counters, 2 * sizeof(unsigned long long)));
+    int rc = device_scratch(g_counters, 2 * sizeof(unsigned long long), &counters);
+    if (rc) return rc;
     cudaStream_t s = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(counters, 0, 2 * sizeof(unsigned long long), s);
     if (e == cudaSuccess) {
@@ -988,7 +1081,6 @@ int absinthe_compare_fields(const double* d_expected, const double* d_actual, in
     unsigned long long host[2] = {0, 0};
     if (e == cudaSuccess) e = cudaMemcpyAsync(host, counters, sizeof(host), cudaMemcpyDeviceToHost, s);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-    cudaFree(counters);
     if (e != cudaSuccess) return fail((int)e, "absinthe_compare_fields: %s", cudaGetErrorString(e));
     *errors = host[0];
     *matches = host[1];

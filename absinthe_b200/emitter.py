@@ -49,9 +49,9 @@ DEFAULTS = {
     "BRANCH": False,             # expensive ?: arms become real (warp-coherent) branches
     "STORE_CS": False,           # outputs written with the evict-first (streaming) cache hint
     "L2_ONCE": False,            # centre-only inputs are staged with an L2 evict-first policy
-    "POLL_WARP": False,          # EXPERIMENTAL, compiles but has not run on hardware yet (no GPU parity case): only
-                                 # warp 0 polls the full-barrier of a stage, the other consumer warps sleep in a
-                                 # named barrier behind it (fewer issue slots burnt on polling)
+    "POLL_WARP": False,          # only warp 0 polls the full-barrier of a stage, the other consumer warps wait in a
+                                 # named barrier behind it (fewer issue slots burnt on polling); parity cases
+                                 # "poll-warp*" in tests/test_parity_gpu.py, A/B in DESIGN.md
     "UNIFORM_WARP": False,       # warp index through __shfl_sync(.., 0): the compiler then knows that the role
                                  # split and the per-warp task loops are warp-uniform (uniform datapath, no
                                  # re-materialised descriptors in "divergent" code)

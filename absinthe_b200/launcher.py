@@ -98,10 +98,11 @@ def check(lib, code, what):
         raise LauncherError("%s failed (%d): %s" % (what, code, (lib.absinthe_last_error() or b"").decode()))
 
 
-def _stream_handle(stream):
+def _stream_handle(stream, device=None):
+    """The raw stream: ``None`` is torch's current stream of ``device`` (of the current device when not given)."""
     if stream is None:
         import torch
-        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
     if isinstance(stream, int):
         return ctypes.c_void_p(stream)
     return ctypes.c_void_p(stream.cuda_stream)
@@ -186,23 +187,23 @@ class Variant:
     # -- execution -----------------------------------------------------------------------
     def apply(self, stream=None, graph=False):
         fn = self.lib.absinthe_variant_apply_graph if graph else self.lib.absinthe_variant_apply
-        check(self.lib, fn(self.handle, _stream_handle(stream)), "absinthe_variant_apply")
+        check(self.lib, fn(self.handle, _stream_handle(stream, self.device)), "absinthe_variant_apply")
 
     def apply_group(self, group, with_halo=True, stream=None):
         check(self.lib, self.lib.absinthe_variant_apply_group(self.handle, group, int(with_halo),
-                                                              _stream_handle(stream)), "apply_group")
+                                                              _stream_handle(stream, self.device)), "apply_group")
 
     def halo_group(self, group, stream=None):
-        check(self.lib, self.lib.absinthe_variant_halo_group(self.handle, group, _stream_handle(stream)),
+        check(self.lib, self.lib.absinthe_variant_halo_group(self.handle, group, _stream_handle(stream, self.device)),
               "halo_group")
 
     def pack_group(self, group, low, high, local_faces=True, stream=None):
         check(self.lib, self.lib.absinthe_variant_pack_group(self.handle, group, low.data_ptr(), high.data_ptr(),
-                                                             int(local_faces), _stream_handle(stream)), "pack_group")
+                                                             int(local_faces), _stream_handle(stream, self.device)), "pack_group")
 
     def unpack_group(self, group, low, high, stream=None):
         check(self.lib, self.lib.absinthe_variant_unpack_group(self.handle, group, low.data_ptr(), high.data_ptr(),
-                                                               _stream_handle(stream)), "unpack_group")
+                                                               _stream_handle(stream, self.device)), "unpack_group")
 
     def group_outputs(self, group):
         n = self.lib.absinthe_variant_group_outputs(self.handle, group)
@@ -215,7 +216,7 @@ class Variant:
         """The reference's measurement loop; returns (total_ms[runs], halo_ms[runs])."""
         total = (ctypes.c_float * runs)()
         halo = (ctypes.c_float * runs)()
-        check(self.lib, self.lib.absinthe_variant_run(self.handle, _stream_handle(stream), runs, int(flush),
+        check(self.lib, self.lib.absinthe_variant_run(self.handle, _stream_handle(stream, self.device), runs, int(flush),
                                                       int(training), total, halo), "absinthe_variant_run")
         return list(total), list(halo)
 
@@ -226,7 +227,7 @@ class Variant:
         fn = self.lib.absinthe_variant_apply_host if wait else self.lib.absinthe_variant_apply_host_async
         # ``None`` entries keep the device-resident field (constants bound once)
         check(self.lib, fn(self.handle, _pointer_array([0 if t is None else t.data_ptr() for t in host_inputs]),
-                           _pointer_array([t.data_ptr() for t in host_outputs]), _stream_handle(stream)),
+                           _pointer_array([t.data_ptr() for t in host_outputs]), _stream_handle(stream, self.device)),
               "apply_host")
         self._host = (self._host + [(host_inputs, host_outputs)])[-2:]   # keep the buffers of steps in flight alive
 
@@ -241,18 +242,22 @@ class Variant:
 # ---- field helpers -----------------------------------------------------------------------
 
 def make_periodic(tensor, dims, stream=None, ik_only=False):
+    import torch
     lib = load_library()
     fn = lib.absinthe_make_periodic_ik if ik_only else lib.absinthe_make_periodic
-    check(lib, fn(tensor.data_ptr(), *dims, _stream_handle(stream)), "absinthe_make_periodic")
+    with torch.cuda.device(tensor.device):       # the field helpers launch on the current device: the tensor's
+        check(lib, fn(tensor.data_ptr(), *dims, _stream_handle(stream, tensor.device)), "absinthe_make_periodic")
 
 
 def compare_fields(expected, actual, dims, tolerance=1e-7, stream=None):
     """(errors, matches) over the interior with the reference's relative test (ref template_tiling.cpp:383-392)."""
     lib = load_library()
+    import torch
     errors, matches = ctypes.c_ulonglong(0), ctypes.c_ulonglong(0)
-    check(lib, lib.absinthe_compare_fields(expected.data_ptr(), actual.data_ptr(), *dims, tolerance,
-                                           ctypes.byref(errors), ctypes.byref(matches), _stream_handle(stream)),
-          "absinthe_compare_fields")
+    with torch.cuda.device(expected.device):
+        check(lib, lib.absinthe_compare_fields(expected.data_ptr(), actual.data_ptr(), *dims, tolerance,
+                                               ctypes.byref(errors), ctypes.byref(matches),
+                                               _stream_handle(stream, expected.device)), "absinthe_compare_fields")
     return errors.value, matches.value
 
 

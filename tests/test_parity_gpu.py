@@ -39,6 +39,8 @@ OPTIONS = [
                                "UNIFORM_WARP": True}),
     ("stream-k", {"STREAM_K": True}),
     ("stream-k-inline", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "PREFETCH": 1}),
+    ("poll-warp", {"INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "POLL_WARP": True, "STAGES": 3}),
+    ("poll-warp-generic", {"POLL_WARP": True, "THREADS": 128}),
     ("column", {"STREAM_K": "regs"}),
     ("column-rj2-planes2-halo", {"STREAM_K": "regs", "BLOCK": (2, 1), "COLUMN": {"WARPS": (1, 2), "PLANES": 2},
                                  "FUSE_HALO": True}),
