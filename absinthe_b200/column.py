@@ -95,8 +95,10 @@ class ColumnPlan:
         # __launch_bounds__ yields is 16384 / (32 * ceil(warps / 4)) -- 255 up to 8 warps, 168 up to 12, 128 up
         # to 16, producer warp included.  MAXREG (__maxnreg__) only serves to lower it.
         self.maxreg = col.get("MAXREG")
-        # producers start the n-th work item of every CTA together (see template_column.cu)
-        self.wave_sync = bool(col.get("WAVE_SYNC", True))
+        # WAVE_SYNC: producers start the n-th work item of every CTA together (see template_column.cu).  Measured:
+        # the halo reads then hit L2 (dram reads 10.4 -> 8.2 GB on fused fast waves) but CTAs marching through the
+        # same planes at the same time run at half the speed (5.4 vs 2.7 ms) -- off by default.
+        self.wave_sync = bool(col.get("WAVE_SYNC", False))
         self.fuse_halo = bool(opts["FUSE_HALO"]) and all(s >= 2 * h for s, h in zip(dims, self.H))
         self.acc = {n: A.stencil_accesses(self.by_name[n]["LAMBDA"]) for n in self.names}
         self._schedule()

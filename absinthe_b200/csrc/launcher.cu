@@ -503,10 +503,20 @@ int encode_map(const absinthe_variant* v, const Arg& a, double* base, CUtensorMa
     cuuint64_t strides[2] = {(cuuint64_t)g.row() * 8, (cuuint64_t)g.plane() * 8};
     cuuint32_t box[3] = {a.box[0], a.box[1], a.box[2]};
     cuuint32_t elem[3] = {1, 1, 1};
+    // L2 promotion: how much the L2 fetches around a requested sector.  256 B suits boxes whose rows are
+    // read whole by neighbouring work items soon after; ABSINTHE_TMA_L2_PROMOTION=0..3 (none, 64, 128,
+    // 256 B) overrides it for A/B runs.
+    CUtensorMapL2promotion promotion = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* env = std::getenv("ABSINTHE_TMA_L2_PROMOTION")) {
+        const int level = std::atoi(env);
+        promotion = level <= 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                               : (level == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                             : (level == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                           : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    }
     DRV(g_drv.TensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, dims, strides, box,
                                    elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
+                                   promotion, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE));
     return 0;
 }
 

@@ -8,7 +8,10 @@ fused/tiled variant through the C-ABI launcher, periodic halo updates included. 
 Mpoints/s, a point being one grid point taken through one whole sequence.
 
 ``--impl reference`` times the reference's own OpenMP build (oracle/_ref, built in the
-development container) of the same variants on the host cores, on a bounded slab of the domain.
+development container) of the same variants on all host cores, on the full 1024 x 1024 x 80 domain
+(the ``cpu_baseline`` leg of the GPU arm uses a 1024 x 1024 x 8 slab of it to stay within seconds).
+``--check`` runs one step of the bench variants (through the slab exchange when N > 1) and compares
+windows at the domain corners and at the j-seams of the slabs with the CPU oracle.
 """
 
 import argparse
@@ -49,6 +52,37 @@ def workload_programs(domain=DOMAIN):
     return out
 
 
+REF_RUNS = 6                        # printed runs compiled into the reference binaries (2 x RUNS executions)
+
+
+def extra_programs():
+    """Variants timed for the ``extras`` block (outside ``value``): advection at the bench domain, auto-tuned
+    and with the HAND-style one-tile-per-plane tiling (ref advection.py:145-160), and the three sequences on the
+    reference's default 64 x 64 x 60 domain (BASELINE.json configs[0], [2])."""
+    from absinthe_b200 import programs as P
+    tuned = json.load(open(TUNED)) if os.path.exists(TUNED) else {}
+    out = []
+    adv = P.KERNELS["advection"][1]()
+    cfg = tuned.get("advection", {"assignment": [0] * 8, "tiles": [[2, 128, 80]], "cuda": {}})
+    auto = P.make_program("advection", P.split_sequence(adv, cfg["assignment"]), [tuple(t) for t in cfg["tiles"]],
+                          domain=DOMAIN, variant="advection-auto")
+    auto["CUDA"] = dict(cfg.get("cuda", {}))
+    hand = P.make_program("advection", [adv], [(1, 1, DOMAIN[2])], domain=DOMAIN, variant="advection-hand")
+    hand["CUDA"] = dict(cfg.get("cuda", {}))
+    out += [("advection:auto", auto), ("advection:hand(1,1,Z)", hand)]
+    small = {"INLINE": "all", "FUSE_HALO": True, "BLOCK": (2, 1), "THREADS": 256}
+    for kernel, groups, cuda in (
+            ("diffusion", None, dict(small, SHUFFLE=True)),
+            ("advection", None, small),
+            ("fastwaves", "split", dict(small, BLOCK=(1, 2)))):
+        seq = P.KERNELS[kernel][1]()
+        groups = [seq[:6], seq[6:]] if groups == "split" else [seq]
+        program = P.make_program(kernel, groups, [(2, 16, 5)] * len(groups), variant=kernel + "-64x64x60")
+        program["CUDA"] = dict(cuda)
+        out.append(("small:" + kernel, program))
+    return out
+
+
 # untuned fall-backs: diffusion one group per field, fast waves the HAND/AUTO two-group split
 DEFAULT_VARIANTS = {
     "diffusion": {"assignment": [0] * 4 + [1] * 4 + [2] * 4 + [3] * 4, "tiles": [[8, 64, 80]] * 4},
@@ -71,20 +105,25 @@ def scale_tiles(program, domain):
     return q
 
 
-def prebuild():
-    """Compile everything the default run needs (called from __graft_entry__.build)."""
+def prebuild_variants():
     from absinthe_b200.generator import build_variant
     from absinthe_b200 import programs as P
-    for _, program in workload_programs():
+    for _, program in workload_programs() + extra_programs():
         build_variant(P.clone(program))
+
+
+def prebuild():
+    """Compile everything the default run needs (called from __graft_entry__.build)."""
+    prebuild_variants()
     try:
         from oracle import build_ref
         if build_ref.available():
             for name, program in workload_programs():
-                slab = scale_tiles(program, CPU_SLAB)
-                slab["RUNS"] = 6
-                slab["VARIANT"] = program["VARIANT"]
-                build_ref.build_binary(slab, "bench_" + name)
+                for prefix, domain in (("bench_", CPU_SLAB), ("benchfull_", DOMAIN)):
+                    sample = scale_tiles(program, domain)
+                    sample["RUNS"] = REF_RUNS
+                    sample["VARIANT"] = program["VARIANT"]
+                    build_ref.build_binary(sample, prefix + name)
     except Exception as exc:
         print("reference build skipped:", exc)
 
@@ -119,13 +158,17 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
+        return self.summary(*self.window)
+
+    def summary(self, lo, hi, warm=None):
+        """Clock statistics of the samples between two ``time.monotonic()`` stamps."""
         sm, reasons, sm_max = [], set(), None
-        lo, hi, warm = self.window
         timed = [row for t, row in self.rows if lo is not None and hi is not None and lo <= t <= hi + 0.02]
         # a timed region shorter than a few sampling periods holds too few samples: then the warm-up steps
         # that ran right before it (same kernels, same load) are counted too, and the line says so
         window = "timed region" if len(timed) >= 3 else "warm-up + timed region"
-        for row in (timed if len(timed) >= 3 else [row for t, row in self.rows if warm is None or t >= warm]):
+        for row in (timed if len(timed) >= 3 else [row for t, row in self.rows if (warm is None or t >= warm)
+                                                    and (hi is None or t <= hi + 0.02)]):
             try:
                 sm.append(float(row[0]))
                 sm_max = float(row[1])
@@ -140,16 +183,16 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm), "window": window, "period_ms": 20}
 
 
-def cpu_reference_time(name, steps, warmup):
+def cpu_reference_time(name, steps, warmup, prefix="bench_"):
     """Run the prebuilt reference binary of ``name``; returns (median total ms, samples, threads)."""
-    exe = os.path.join(REF_DIR, "bench_" + name)
+    exe = os.path.join(REF_DIR, prefix + name)
     if not os.path.exists(exe):
         return None
     threads = os.cpu_count() or 1
     env = dict(os.environ, OMP_PLACES="cores", OMP_PROC_BIND="close", OMP_NUM_THREADS=str(threads),
                OMP_STACKSIZE="512M")
     proc = subprocess.run("ulimit -s unlimited; exec " + exe, shell=True, env=env, capture_output=True, text=True,
-                          timeout=900)
+                          timeout=1500)
     totals = [float(line.split(":")[1]) for line in proc.stdout.splitlines()
               if line.startswith("   - total time")]
     if not totals:
@@ -170,13 +213,17 @@ def cpu_port_time(name, program):
     return (time.perf_counter() - t0) * 1e3
 
 
-def cpu_baseline(steps=3, warmup=1):
-    """Mpoints/s of the CPU arm on the bounded slab; prefers the real reference build."""
+def cpu_baseline(steps=3, warmup=1, full=False):
+    """Mpoints/s of the CPU arm; prefers the real reference build.  ``full``: the whole bench domain (the
+    ``--impl reference`` arm), else a bounded 1024 x 1024 x 8 slab of it (same per-point work)."""
     from absinthe_b200 import programs as P
-    points = CPU_SLAB[0] * CPU_SLAB[1] * CPU_SLAB[2]
+    domain = DOMAIN if full else CPU_SLAB
+    points = domain[0] * domain[1] * domain[2]
     total_ms, kind, threads, detail, timed = 0.0, "reference", 1, {}, steps
     for name, program in workload_programs():
-        got = cpu_reference_time(name, steps, warmup)
+        got = cpu_reference_time(name, steps, warmup, "benchfull_" if full else "bench_")
+        if got is None and full:                 # no full-size binary shipped: the slab, and the line says so
+            return cpu_baseline(steps, warmup, full=False)
         if got is None:
             kind = "port"
             break
@@ -185,33 +232,37 @@ def cpu_baseline(steps=3, warmup=1):
         detail[name] = got[0]
     if kind == "port":
         total_ms, threads, detail = 0.0, 1, {}
-        small = (256, 256, 8)
-        points = small[0] * small[1] * small[2]
+        domain = (256, 256, 8)
+        points = domain[0] * domain[1] * domain[2]
         for name, program in workload_programs():
-            ms = cpu_port_time(name, scale_tiles(program, small))
+            ms = cpu_port_time(name, scale_tiles(program, domain))
             total_ms += ms
             detail[name] = ms
-        sample = "sequential oracle port, %dx%dx%d slab, one pass per sequence" % small
+        sample = "sequential oracle port, %dx%dx%d slab, one pass per sequence" % domain
     else:
-        sample = ("reference OpenMP build (g++ -O3 -ffast-math -fopenmp) of the same variants on a "
-                  "%dx%dx%d slab, median of %d timed runs per sequence" % (CPU_SLAB + (timed,)))
+        sample = ("reference OpenMP build (g++ -O3 -ffast-math -fopenmp) of the same variants on %s, "
+                  "median of %d timed runs per sequence" % (
+                      "the full %dx%dx%d domain" % domain if domain == DOMAIN else "a %dx%dx%d slab" % domain, timed))
     value = 2 * points / (total_ms * 1e-3) / 1e6
     return {"value": value, "unit": "Mpoints/s", "cores": threads, "kind": kind, "sample": sample,
-            "ms_per_sequence": detail}
+            "sample_domain": list(domain), "ms_per_sequence": detail}
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    base = cpu_baseline(steps=args.steps, warmup=args.warmup)
-    points = CPU_SLAB[0] * CPU_SLAB[1] * CPU_SLAB[2]
+    base = cpu_baseline(steps=args.steps, warmup=args.warmup, full=True)
+    points = base["sample_domain"][0] * base["sample_domain"][1] * base["sample_domain"][2]
+    config = workload_config(args.gpus)
+    config["reference_sample"] = base["sample"]
+    config["same_domain_as_gpu_arm"] = base["sample_domain"] == list(DOMAIN)
     line = {
         "impl": "reference", "metric": "fused_sequence_throughput", "value": base["value"], "unit": "Mpoints/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 2 * points / base["value"] / 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args.gpus), "cpu_baseline": base,
+        "config": config, "cpu_baseline": base,
         "e2e": {"value": base["value"], "unit": "Mpoints/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -255,9 +306,7 @@ def run_gpu_arm(args):
     sampler.start()
     if local == 0:                                 # one rank builds, the others wait for the cache
         build_launcher()
-        from absinthe_b200.generator import build_variant
-        for _, program in workload_programs():
-            build_variant(P.clone(program))
+        prebuild_variants()
     if world > 1:
         dist.barrier()
 
@@ -336,13 +385,49 @@ def run_gpu_arm(args):
     torch.cuda.synchronize()
     sampler.mark(1)
     elapsed_ms = start.elapsed_time(stop)
-    clocks = sampler.stop()
+    clocks = sampler.summary(*sampler.window)
+
     if world > 1:
         t = torch.tensor([elapsed_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         elapsed_ms = float(t.item())
     ms_per_step = elapsed_ms / args.steps
     value = 2 * points * world / (ms_per_step * 1e-3) / 1e6
+
+    # sustained: the same step back to back for >= `--sustain` seconds (the board settles at its power cap); the
+    # last batch is reported, with per-kernel events.  The batch count is fixed up front: every rank runs the same.
+    sustained, sustained_records = None, []
+    if args.sustain > 0:
+        per_batch = 25
+        n_batches = max(2, int(args.sustain * 1e3 / (ms_per_step * per_batch)) + 1)
+        t_begin = time.monotonic()
+        for batch in range(n_batches):
+            last = batch == n_batches - 1
+            if last:
+                torch.cuda.synchronize()
+                t_last = time.monotonic()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(per_batch):
+                step(sustained_records if last else None)
+            if last:
+                for item in variants:
+                    if item["exchange"] is not None:
+                        for g in range(1, item["v"].n_groups + 1):
+                            item["exchange"].wait(g)
+            b.record()
+        torch.cuda.synchronize()
+        t_end = time.monotonic()
+        sustained_ms = a.elapsed_time(b) / per_batch
+        if world > 1:
+            t = torch.tensor([sustained_ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sustained_ms = float(t.item())
+        sustained = {"ms_per_step": round(sustained_ms, 4), "seconds": round(t_end - t_begin, 2),
+                     "steps": n_batches * per_batch,
+                     "value": round(2 * points * world / (sustained_ms * 1e-3) / 1e6, 1), "unit": "Mpoints/s",
+                     "clocks": sampler.summary(t_last, t_end)}
+    sampler.stop()
 
     # per-kernel durations from the events of the timed region
     kernel_ms, halo_ms = {}, {}
@@ -369,12 +454,34 @@ def run_gpu_arm(args):
     traffic = None
     if os.path.exists(TRAFFIC):
         traffic = json.load(open(TRAFFIC)).get(dominant[0])
+    if sustained is not None:
+        sustained["step_frac"] = round(sum(item["bytes_per_point"] for item in variants) * points
+                                       / (sustained["ms_per_step"] * 1e-3) / 1e9 / peak, 4)
+        hot = {}
+        for name, g, a, b, c in sustained_records:
+            hot.setdefault((name, g), []).append(a.elapsed_time(b))
+        kernels = {}
+        for item in variants:
+            for g in range(1, item["v"].n_groups + 1):
+                k = statistics.mean(hot[(item["name"], g)])
+                gbs = item["group_bytes"][g - 1] * points / (k * 1e-3) / 1e9
+                kernels[item["group_names"][g - 1]] = {"kernel_ms": round(k, 4), "GBps": round(gbs, 1),
+                                                       "frac": round(gbs / peak, 4)}
+        sustained["kernels"] = kernels
+        sustained["frac"] = kernels[dominant[0]]["frac"]          # the roofline kernel, in the heated state
     step_bytes = sum(item["bytes_per_point"] for item in variants) * points
     roofline = {"bound": "hbm", "kernel": dominant[0], "achieved": round(dominant[2], 1), "peak": peak,
                 "unit": "GB/s", "frac": round(dominant[2] / peak, 4), "traffic": traffic, "peak_kind": peak_kind,
                 "step_GBps": round(step_bytes * world / (ms_per_step * 1e-3) / 1e9, 1),
                 "step_frac": round(step_bytes / (ms_per_step * 1e-3) / 1e9 / peak, 4),
                 "frac_of_8TBps": round(dominant[2] / 8000.0, 4)}
+
+    extras = None
+    if world == 1 and not args.no_extras:
+        try:
+            extras = measure_extras(peak)
+        except Exception as exc:                       # extras never cost the headline line
+            extras = {"error": str(exc)[:300]}
 
     # end to end through the public API with HOST buffers (pinned), copies inside the timed region
     launches = sum(item["v"].launches for item in variants) * args.steps
@@ -434,7 +541,8 @@ def run_gpu_arm(args):
             "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
-            "gpu_launches": launches, "roofline": roofline, "breakdown": breakdown,
+            "gpu_launches": launches, "roofline": roofline, "breakdown": breakdown, "sustained": sustained,
+            "extras": extras,
             "variants": {item["name"]: workload_programs()[n][1]["VARIANT"] for n, item in enumerate(variants)},
         }
         if world == 1 and not args.no_cpu:
@@ -446,6 +554,87 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def measure_extras(peak):
+    """Driver-visible numbers for BASELINE.json configs[0..3], outside ``value`` (see ``extra_programs``)."""
+    import torch
+    from absinthe_b200 import programs as P
+    from absinthe_b200.analysis import algorithmic_bytes_per_point, analyse
+    from absinthe_b200.launcher import Variant, make_periodic
+    out = {}
+    gen = torch.Generator(device="cuda").manual_seed(99)
+    for label, program in extra_programs():
+        v = Variant.from_program(P.clone(program))
+        dims = (v.X, v.Y, v.Z, v.HX, v.HY, v.HZ)
+        ins = []
+        for _ in v.inputs:
+            t = torch.rand(v.shape, dtype=torch.float64, device="cuda", generator=gen) + 0.5
+            make_periodic(t, dims)
+            ins.append(t)
+        outs = [v.empty_field() for _ in v.outputs]
+        v.bind(ins, outs)
+        small = label.startswith("small:")
+        reps = 300 if small else 12
+        for _ in range(3):
+            v.apply(graph=small)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            v.apply(graph=small)
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / reps
+        row = {"domain": [v.X, v.Y, v.Z], "variant": program["VARIANT"], "launches": v.launches,
+               "mpoints_s": round(v.points / ms / 1e3, 1)}
+        if small:                                   # the whole domain sits in L2: this is a launch latency
+            row["graph_us"] = round(ms * 1e3, 2)
+        else:
+            bpp = algorithmic_bytes_per_point(analyse(P.clone(program)))
+            gbs = bpp * v.points / (ms * 1e-3) / 1e9
+            row.update(ms=round(ms, 4), bytes_per_point=bpp, GBps=round(gbs, 1), frac=round(gbs / peak, 4))
+        out[label] = row
+        v.close()
+        del ins, outs
+        torch.cuda.empty_cache()
+    return out
+
+
+def run_check_mode(args):
+    """``--check``: one step of the bench variants on every rank, windows (corners, middle, both j-seams of the
+    slab) against the CPU oracle.  The oracle is the checker here; nothing of this is timed."""
+    import torch
+    import torch.distributed as dist
+    from absinthe_b200.build import build_launcher
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from seam_check import run_check
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    if local == 0:
+        build_launcher()
+        prebuild_variants()
+    if world > 1:
+        dist.barrier()
+    report = run_check(workload_programs(), world, rank, local)
+    reports = [report]
+    if world > 1:
+        reports = [None] * world
+        dist.all_gather_object(reports, report)
+    if rank == 0:
+        emit({"check": "ok" if all(r["ok"] for r in reports) else "FAILED", "n_gpus": world,
+              "config": workload_config(world), "windows_per_rank": len(report["windows"]),
+              "failed": [w for r in reports for w in r["windows"] if not w["ok"]],
+              "rows_compared": sum(w["rows"] for r in reports for w in r["windows"])})
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    if not report["ok"]:
+        sys.exit(1)
 
 
 RESULT = sys.stdout
@@ -472,12 +661,19 @@ def main():
     parser.add_argument("--warmup", type=int, default=3)
     parser.add_argument("--impl", default="absinthe_b200", choices=["absinthe_b200", "reference"])
     parser.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    parser.add_argument("--no-extras", action="store_true", help="skip the extras block (advection, 64x64x60 latencies)")
+    parser.add_argument("--sustain", type=float, default=2.0,
+                        help="seconds of back-to-back steps after the timed region for the sustained sub-record (0 = off)")
+    parser.add_argument("--check", action="store_true",
+                        help="run one step of the bench variants and compare corner and seam windows with the CPU oracle")
     parser.add_argument("--e2e-upload", default="full", choices=["full", "interior"],
                         help="end-to-end leg: upload whole padded fields, or only the interiors of the host inputs "
                              "(the library rebuilds their periodic halos on the device; measured: same step time)")
     args = parser.parse_args()
     claim_stdout()
-    if args.impl == "reference":
+    if args.check:
+        run_check_mode(args)
+    elif args.impl == "reference":
         run_reference_arm(args)
     else:
         run_gpu_arm(args)

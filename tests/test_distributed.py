@@ -1,5 +1,6 @@
 """Multi-rank halo exchange: the protocol on CPU (gloo, world_size 2) and the full path on >= 2 GPUs."""
 
+import json
 import os
 import subprocess
 import sys
@@ -106,3 +107,28 @@ def test_two_gpus_match_one(launcher_lib):
     proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT)
     assert proc.returncode == 0, proc.stdout[-3000:] + proc.stderr[-3000:]
     assert "multi-gpu parity ok" in proc.stdout
+
+
+@pytest.mark.gpu
+def test_bench_variants_match_the_oracle_on_one_gpu(launcher_lib):
+    """``bench.py --check`` at N = 1: the tuned 1024 x 1024 x 80 variants against the windowed oracle."""
+    proc = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--check"], capture_output=True,
+                          text=True, timeout=900, cwd=ROOT)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
+    report = json.loads(proc.stdout.strip().splitlines()[-1])
+    assert report["check"] == "ok" and report["rows_compared"] > 0 and not report["failed"]
+
+
+@pytest.mark.gpu
+def test_bench_variants_match_the_oracle_across_two_slabs(launcher_lib):
+    """The combination the scaling bench times -- tuned variants, fused periodic copies, per-group tile shapes,
+    ``SlabExchange.update_async`` at 1024 x 1024 x 80 per rank -- with seam windows (the rows either side of both
+    slab edges, halo rows included) compared with the oracle on every rank."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run with gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29613", os.path.join(ROOT, "bench.py"), "--check", "--gpus", "2"]
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
+    report = json.loads([line for line in proc.stdout.splitlines() if line.startswith("{")][-1])
+    assert report["check"] == "ok" and report["n_gpus"] == 2 and not report["failed"]
