@@ -267,6 +267,74 @@ int sm_count() {
     return cached[dev];
 }
 
+// ---- P2P slab exchange -------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long load_flag(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void store_flag(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// PUT: the first HY interior rows of every field go to the previous rank's "from next" buffer, the last HY
+// interior rows to the next rank's "from previous" buffer ([field][plane][HY][row], through peer-mapped
+// pointers); the last block to finish raises both arrival flags to `epoch`.
+__global__ void put_kernel(FieldList fields, Geometry g, double* __restrict__ to_prev, double* __restrict__ to_next,
+                           unsigned long long* flag_at_prev, unsigned long long* flag_at_next, unsigned* done,
+                           unsigned long long epoch) {
+    const long row = g.row(), plane = g.plane();
+    const long per_field = g.planes() * g.HY * row;
+    const long total = 2 * fields.count * per_field;
+    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < total; n += (long)gridDim.x * blockDim.x) {
+        const int side = (int)(n / (fields.count * per_field));
+        const long m = n % (fields.count * per_field);
+        const int f = (int)(m / per_field);
+        const long r = m % per_field;
+        const long k = r / (g.HY * row), q = r % (g.HY * row);
+        const long j0 = side ? g.Y : g.HY;                 // last / first HY interior rows (padded row index)
+        const double v = fields.ptr[f][k * plane + (j0 + q / row) * row + q % row];
+        (side ? to_next : to_prev)[m] = v;
+    }
+    __threadfence_system();                                 // this thread's remote stores are out
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (atomicAdd(done, 1u) == gridDim.x - 1) {         // every block's stores are out
+            *done = 0;
+            __threadfence_system();
+            store_flag(flag_at_prev, epoch);
+            store_flag(flag_at_next, epoch);
+        }
+    }
+}
+
+// WAIT: spin (bounded) until both neighbours have raised this rank's flags to `epoch`, then copy the rows they
+// stored into the low / high j-halo.
+__global__ void wait_kernel(FieldList fields, Geometry g, const double* __restrict__ from_prev,
+                            const double* __restrict__ from_next, const unsigned long long* flags,
+                            unsigned long long epoch) {
+    if (threadIdx.x == 0) {
+        unsigned long long spins = 0;
+        while (load_flag(flags) < epoch || load_flag(flags + 1) < epoch) {
+            __nanosleep(200);
+            if (++spins > (1ull << 24)) __trap();           // a neighbour that never arrives ends in an error, not a hang
+        }
+    }
+    __syncthreads();
+    const long row = g.row(), plane = g.plane();
+    const long per_field = g.planes() * g.HY * row;
+    const long total = 2 * fields.count * per_field;
+    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < total; n += (long)gridDim.x * blockDim.x) {
+        const int side = (int)(n / (fields.count * per_field));
+        const long m = n % (fields.count * per_field);
+        const int f = (int)(m / per_field);
+        const long r = m % per_field;
+        const long k = r / (g.HY * row), q = r % (g.HY * row);
+        const long j0 = side ? g.Y + g.HY : 0;              // high / low halo rows
+        fields.ptr[f][k * plane + (j0 + q / row) * row + q % row] = (side ? from_next : from_prev)[m];
+    }
+}
+
 int launch_grid(long items, int threads) {
     long blocks = (items + threads - 1) / threads;
     return (int)std::max(1L, std::min(blocks, (long)sm_count() * 16));
@@ -370,6 +438,23 @@ struct absinthe_variant {
     unsigned long long host_issued = 0, host_waited = 0;  // async host steps enqueued / waited for
     bool host_interior = false;                           // upload interiors only, rebuild the halos on the device
     std::vector<cudaEvent_t> events;
+    // P2P slab exchange (absinthe_comm_*): this rank's window and the neighbours' windows
+    struct CommGroup {
+        int group = 0;
+        size_t face_doubles = 0;                 // one direction of one PUT: fields x planes x HY x row
+        size_t data = 0;                         // offset (doubles) of [parity][from_prev | from_next] buffers
+        size_t flags = 0;                        // offset (doubles) of {from_prev, from_next} arrival epochs
+        unsigned long long put = 0, waited = 0;  // PUTs enqueued / WAITs enqueued
+        cudaEvent_t unpacked = nullptr;          // recorded after the WAIT kernel of the latest epoch
+    };
+    int comm_rank = 0, comm_ranks = 0;
+    double* window = nullptr;                    // own window (cudaMalloc, IPC exported)
+    size_t window_doubles = 0;
+    double* window_prev = nullptr;               // neighbours' windows (IPC mapped, or own window when n = 1)
+    double* window_next = nullptr;
+    bool prev_mapped = false, next_mapped = false;
+    unsigned* put_done = nullptr;                // block counter of the PUT kernels (one per group)
+    std::vector<CommGroup> comm_groups;
 };
 
 namespace {
@@ -661,6 +746,7 @@ void absinthe_variant_free(absinthe_variant* v) {
     for (cudaEvent_t e : v->ev_out)
         if (e) cudaEventDestroy(e);
     for (cudaEvent_t e : v->events) cudaEventDestroy(e);
+    absinthe_comm_destroy(v);
     for (Field& f : v->fields)
         if (f.owned && f.ptr) cudaFree(f.ptr);
     for (Group& g : v->groups)
@@ -1094,6 +1180,174 @@ int absinthe_compare_fields(const double* d_expected, const double* d_actual, in
     if (e != cudaSuccess) return fail((int)e, "absinthe_compare_fields: %s", cudaGetErrorString(e));
     *errors = host[0];
     *matches = host[1];
+    return 0;
+}
+
+}  // extern "C"
+
+// ---- multi-GPU halo exchange (see include/absinthe_b200.h) ---------------------------------------
+extern "C" {
+
+int absinthe_comm_create(absinthe_variant* v, int rank, int nranks, unsigned char handle[ABSINTHE_COMM_HANDLE_BYTES]) {
+    if (!v || !handle) return fail(-3, "absinthe_comm_create: null argument");
+    if (nranks < 1 || rank < 0 || rank >= nranks) return fail(-3, "absinthe_comm_create: rank %d of %d", rank, nranks);
+    static_assert(sizeof(cudaIpcMemHandle_t) == ABSINTHE_COMM_HANDLE_BYTES, "IPC handle size");
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
+    absinthe_comm_destroy(v);
+    const Geometry& g = v->geo;
+    if (g.Y < g.HY) return fail(-3, "slab of %d rows is thinner than the halo", g.Y);
+    size_t cursor = 0;
+    for (const Group& grp : v->groups) {
+        if (grp.halo_fields.empty()) continue;
+        absinthe_variant::CommGroup c;
+        c.group = grp.id;
+        c.face_doubles = grp.halo_fields.size() * (size_t)g.planes() * g.HY * g.row();
+        c.flags = cursor;
+        cursor += 16;                                     // a 128-byte line for the two arrival epochs
+        c.data = cursor;
+        cursor += 4 * ((c.face_doubles + 15) / 16 * 16);  // [parity][from_prev | from_next]
+        v->comm_groups.push_back(c);
+    }
+    v->window_doubles = std::max<size_t>(cursor, 16);
+    RT(cudaMalloc(&v->window, v->window_doubles * sizeof(double)));
+    RT(cudaMemset(v->window, 0, v->window_doubles * sizeof(double)));
+    RT(cudaMalloc(&v->put_done, sizeof(unsigned) * std::max<size_t>(v->comm_groups.size(), 1)));
+    RT(cudaMemset(v->put_done, 0, sizeof(unsigned) * std::max<size_t>(v->comm_groups.size(), 1)));
+    for (auto& c : v->comm_groups) RT(cudaEventCreateWithFlags(&c.unpacked, cudaEventDisableTiming));
+    RT(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    RT(cudaIpcGetMemHandle(&h, v->window));
+    std::memcpy(handle, &h, sizeof(h));
+    v->comm_rank = rank;
+    v->comm_ranks = nranks;
+    return 0;
+}
+
+int absinthe_comm_connect(absinthe_variant* v, const unsigned char* prev_handle, const unsigned char* next_handle) {
+    if (!v || !v->window) return fail(-3, "absinthe_comm_connect: no window (call absinthe_comm_create first)");
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
+    if (v->comm_ranks == 1) {                             // both neighbours are this rank
+        v->window_prev = v->window_next = v->window;
+        return 0;
+    }
+    if (!prev_handle || !next_handle) return fail(-3, "absinthe_comm_connect: null handle");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, prev_handle, sizeof(h));
+    void* mapped = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail((int)e, "cannot map the window of rank %d: %s", (v->comm_rank + v->comm_ranks - 1) % v->comm_ranks, cudaGetErrorString(e));
+    v->window_prev = (double*)mapped;
+    v->prev_mapped = true;
+    if (v->comm_ranks == 2) {                             // the same neighbour on both sides
+        v->window_next = v->window_prev;
+        return 0;
+    }
+    std::memcpy(&h, next_handle, sizeof(h));
+    e = cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) return fail((int)e, "cannot map the window of rank %d: %s", (v->comm_rank + 1) % v->comm_ranks, cudaGetErrorString(e));
+    v->window_next = (double*)mapped;
+    v->next_mapped = true;
+    return 0;
+}
+
+int absinthe_comm_destroy(absinthe_variant* v) {
+    if (!v) return 0;
+    if (v->window) cudaDeviceSynchronize();
+    if (v->prev_mapped && v->window_prev) cudaIpcCloseMemHandle(v->window_prev);
+    if (v->next_mapped && v->window_next) cudaIpcCloseMemHandle(v->window_next);
+    for (auto& c : v->comm_groups)
+        if (c.unpacked) cudaEventDestroy(c.unpacked);
+    if (v->window) cudaFree(v->window);
+    if (v->put_done) cudaFree(v->put_done);
+    v->window = v->window_prev = v->window_next = nullptr;
+    v->put_done = nullptr;
+    v->prev_mapped = v->next_mapped = false;
+    v->comm_groups.clear();
+    v->comm_ranks = 0;
+    return 0;
+}
+
+static int comm_group(absinthe_variant* v, int group, absinthe_variant::CommGroup** out, Group** grp, size_t* index) {
+    int rc = require_bound(v);
+    if (rc) return rc;
+    if (!v->window_prev || !v->window_next) return fail(-3, "variant '%s': exchange not connected", v->name.c_str());
+    for (size_t n = 0; n < v->comm_groups.size(); ++n)
+        if (v->comm_groups[n].group == group) {
+            *out = &v->comm_groups[n];
+            *index = n;
+            for (Group& g : v->groups)
+                if (g.id == group) *grp = &g;
+            return 0;
+        }
+    *out = nullptr;
+    return 0;                                             // a group without outputs has nothing to exchange
+}
+
+int absinthe_variant_put_group(absinthe_variant* v, int group, void* stream) {
+    absinthe_variant::CommGroup* c = nullptr;
+    Group* g = nullptr;
+    size_t index = 0;
+    int rc = comm_group(v, group, &c, &g, &index);
+    if (rc || !c) return rc;
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
+    if (c->put != c->waited)
+        return fail(-6, "group %d: the previous PUT has not been waited for (absinthe_variant_wait_group)", group);
+    cudaStream_t s = (cudaStream_t)stream;
+    FieldList list{};
+    list.count = (int)g->halo_fields.size();
+    for (int n = 0; n < list.count; ++n) list.ptr[n] = v->fields[g->halo_fields[n]].ptr;
+    const Geometry& q = v->geo;
+    if (!g->fused_halo) {                                 // local periodic i and k faces first: they travel with the rows
+        if (!(q.X >= q.HX && q.Z >= q.HZ)) return fail(-3, "extent smaller than halo");
+        long cells = 2L * q.HZ * q.plane() + (long)q.Z * q.Y * 2 * q.HX;
+        periodic_kernel<<<launch_grid(cells, 256), 256, 0, s>>>(list, q, 5);
+    }
+    // the neighbours may only overwrite the buffers of this parity once this rank has unpacked them
+    if (c->waited >= 1) RT(cudaStreamWaitEvent(s, c->unpacked, 0));
+    const unsigned long long epoch = ++c->put;
+    const size_t slot = (c->face_doubles + 15) / 16 * 16;
+    const size_t parity = (size_t)(epoch & 1);
+    // my low rows -> previous rank's "from next" buffer; my high rows -> next rank's "from previous" buffer
+    double* to_prev = v->window_prev + c->data + (2 * parity + 1) * slot;
+    double* to_next = v->window_next + c->data + (2 * parity + 0) * slot;
+    unsigned long long* flag_at_prev = (unsigned long long*)(v->window_prev + c->flags) + 1;
+    unsigned long long* flag_at_next = (unsigned long long*)(v->window_next + c->flags) + 0;
+    long total = 2L * list.count * q.planes() * q.HY * q.row();
+    int blocks = std::min(launch_grid(total, 256), sm_count() * 2);
+    put_kernel<<<blocks, 256, 0, s>>>(list, q, to_prev, to_next, flag_at_prev, flag_at_next, v->put_done + index, epoch);
+    RT(cudaGetLastError());
+    return 0;
+}
+
+int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
+    absinthe_variant::CommGroup* c = nullptr;
+    Group* g = nullptr;
+    size_t index = 0;
+    int rc = comm_group(v, group, &c, &g, &index);
+    if (rc || !c) return rc;
+    if (c->waited == c->put) return 0;                    // nothing outstanding
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    FieldList list{};
+    list.count = (int)g->halo_fields.size();
+    for (int n = 0; n < list.count; ++n) list.ptr[n] = v->fields[g->halo_fields[n]].ptr;
+    const Geometry& q = v->geo;
+    const unsigned long long epoch = c->put;
+    const size_t slot = (c->face_doubles + 15) / 16 * 16;
+    const size_t parity = (size_t)(epoch & 1);
+    const double* from_prev = v->window + c->data + (2 * parity + 0) * slot;
+    const double* from_next = v->window + c->data + (2 * parity + 1) * slot;
+    long total = 2L * list.count * q.planes() * q.HY * q.row();
+    int blocks = std::min(launch_grid(total, 256), sm_count() * 2);
+    wait_kernel<<<blocks, 256, 0, s>>>(list, q, from_prev, from_next,
+                                       (const unsigned long long*)(v->window + c->flags), epoch);
+    RT(cudaGetLastError());
+    RT(cudaEventRecord(c->unpacked, s));
+    c->waited = epoch;
     return 0;
 }
 

@@ -134,3 +134,45 @@ class SlabExchange:
             for work in dist.batch_isend_irecv(ops):
                 work.wait()
         self.unpack_all(group, names, recv_low, recv_high)
+
+
+class P2PExchange:
+    """The same PUT / WAIT protocol inside the launcher: peer-to-peer stores over NVLink, no collective library.
+
+    Every rank creates an exchange window on its GPU (``absinthe_comm_create``), the 64-byte IPC handles travel
+    once through ``torch.distributed`` (any backend: they are host bytes), and from then on a PUT is one kernel
+    that stores this rank's edge rows straight into the neighbours' windows and raises their flags, a WAIT one
+    kernel that waits for the flags and fills the j-halos (``absinthe_variant_put_group`` / ``_wait_group``).
+    Interface of ``SlabExchange``: ``update_async(group)`` = PUT on a side stream, ``wait(group)`` = WAIT on the
+    caller's stream, ``update(group)`` = both.
+    """
+
+    def __init__(self, variant, world, rank, process_group=None):
+        import torch.distributed as dist
+        self.v, self.world, self.rank = variant, world, rank
+        self.prev, self.next = neighbours(rank, world)
+        mine = variant.comm_create(rank, world)
+        handles = [mine]
+        if world > 1:
+            handles = [None] * world
+            dist.all_gather_object(handles, mine, group=process_group)
+        variant.comm_connect(handles[self.prev], handles[self.next])
+        if world > 1:
+            dist.barrier(group=process_group)          # nobody PUTs into a window that is not mapped yet
+        self.comm = None
+
+    def update_async(self, group):
+        import torch
+        if self.comm is None:
+            self.comm = torch.cuda.Stream(device=self.v.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.v.device))
+        self.comm.wait_event(ready)
+        self.v.put_group(group, stream=self.comm)
+
+    def wait(self, group):
+        self.v.wait_group(group)
+
+    def update(self, group):
+        self.v.put_group(group)
+        self.v.wait_group(group)

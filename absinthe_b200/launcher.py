@@ -29,7 +29,10 @@ SYMBOLS = [
     "absinthe_variant_pack_group", "absinthe_variant_unpack_group",
     "absinthe_variant_apply_host_async", "absinthe_variant_wait_host", "absinthe_compare_fields",
     "absinthe_variant_host_interior",
+    "absinthe_comm_create", "absinthe_comm_connect", "absinthe_variant_put_group", "absinthe_variant_wait_group",
+    "absinthe_comm_destroy",
 ]
+COMM_HANDLE_BYTES = 64
 
 
 class LauncherError(RuntimeError):
@@ -88,6 +91,11 @@ def load_library(path=None):
     lib.absinthe_halo_unpack.argtypes = [c.c_void_p, c.c_void_p] + [c.c_int] * 8 + [c.c_void_p]
     lib.absinthe_variant_pack_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_int, c.c_void_p]
     lib.absinthe_variant_unpack_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p]
+    lib.absinthe_comm_create.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_char_p]
+    lib.absinthe_comm_connect.argtypes = [c.c_void_p, c.c_char_p, c.c_char_p]
+    lib.absinthe_variant_put_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p]
+    lib.absinthe_variant_wait_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p]
+    lib.absinthe_comm_destroy.argtypes = [c.c_void_p]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -204,6 +212,24 @@ class Variant:
     def unpack_group(self, group, low, high, stream=None):
         check(self.lib, self.lib.absinthe_variant_unpack_group(self.handle, group, low.data_ptr(), high.data_ptr(),
                                                                _stream_handle(stream, self.device)), "unpack_group")
+
+    # -- multi-GPU exchange (P2P windows, see include/absinthe_b200.h) ------------------------
+    def comm_create(self, rank, nranks):
+        """Allocate this rank's exchange window; returns its 64-byte IPC handle (to be handed to the neighbours)."""
+        handle = ctypes.create_string_buffer(COMM_HANDLE_BYTES)
+        check(self.lib, self.lib.absinthe_comm_create(self.handle, rank, nranks, handle), "absinthe_comm_create")
+        return handle.raw
+
+    def comm_connect(self, prev_handle, next_handle):
+        check(self.lib, self.lib.absinthe_comm_connect(self.handle, prev_handle, next_handle), "absinthe_comm_connect")
+
+    def put_group(self, group, stream=None):
+        check(self.lib, self.lib.absinthe_variant_put_group(self.handle, group, _stream_handle(stream, self.device)),
+              "absinthe_variant_put_group")
+
+    def wait_group(self, group, stream=None):
+        check(self.lib, self.lib.absinthe_variant_wait_group(self.handle, group, _stream_handle(stream, self.device)),
+              "absinthe_variant_wait_group")
 
     def group_outputs(self, group):
         n = self.lib.absinthe_variant_group_outputs(self.handle, group)

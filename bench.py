@@ -281,9 +281,9 @@ def _available_host_bytes():
     return 0
 
 
-def workload_config(gpus):
+def workload_config(gpus, exchange=None):
     return {"workload": "diffusion+fastwaves fused sequences, %dx%dx%d fp64 per GPU, halo 3, periodic" % DOMAIN,
-            "domain_per_gpu": list(DOMAIN), "decomposition": "j-slabs x%d" % gpus,
+            "domain_per_gpu": list(DOMAIN), "decomposition": "j-slabs x%d" % gpus, "exchange": exchange,
             "l2": "inputs (>6 GB per sequence) exceed the 126 MB L2; no flush needed between steps"}
 
 
@@ -310,7 +310,8 @@ def run_gpu_arm(args):
     if world > 1:
         dist.barrier()
 
-    from absinthe_b200.distributed import SlabExchange
+    from absinthe_b200.distributed import P2PExchange, SlabExchange
+    Exchange = P2PExchange if args.exchange == "p2p" else SlabExchange
     variants = []
     gen = torch.Generator(device="cuda").manual_seed(1234 + rank)
     for name, program in workload_programs():
@@ -323,7 +324,7 @@ def run_gpu_arm(args):
             ins.append(t)
         outs = [v.empty_field() for _ in v.outputs]
         v.bind(ins, outs)
-        exchange = SlabExchange(v, world, rank) if world > 1 else None
+        exchange = Exchange(v, world, rank) if world > 1 else None
         analysed = P.clone(program)
         from absinthe_b200.analysis import analyse
         analyse(analysed)
@@ -540,7 +541,7 @@ def run_gpu_arm(args):
             "metric": "fused_sequence_throughput", "value": round(value, 1), "unit": "Mpoints/s", "n_gpus": world,
             "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_per_step, 4),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "config": workload_config(world), "clocks": clocks, "e2e": e2e,
+            "data": "synthetic", "config": workload_config(world, args.exchange if world > 1 else None), "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roofline, "breakdown": breakdown, "sustained": sustained,
             "extras": extras,
             "variants": {item["name"]: workload_programs()[n][1]["VARIANT"] for n, item in enumerate(variants)},
@@ -620,7 +621,7 @@ def run_check_mode(args):
         prebuild_variants()
     if world > 1:
         dist.barrier()
-    report = run_check(workload_programs(), world, rank, local)
+    report = run_check(workload_programs(), world, rank, local, exchange_kind=args.exchange)
     reports = [report]
     if world > 1:
         reports = [None] * world
@@ -664,6 +665,9 @@ def main():
     parser.add_argument("--no-extras", action="store_true", help="skip the extras block (advection, 64x64x60 latencies)")
     parser.add_argument("--sustain", type=float, default=2.0,
                         help="seconds of back-to-back steps after the timed region for the sustained sub-record (0 = off)")
+    parser.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                        help="halo exchange of the multi-GPU run: peer-to-peer windows inside the launcher "
+                             "(absinthe_variant_put_group / _wait_group) or pack + NCCL send/recv + unpack")
     parser.add_argument("--check", action="store_true",
                         help="run one step of the bench variants and compare corner and seam windows with the CPU oracle")
     parser.add_argument("--e2e-upload", default="full", choices=["full", "interior"],

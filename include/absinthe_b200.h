@@ -160,6 +160,36 @@ int absinthe_variant_unpack_group(absinthe_variant* v, int group, const double* 
 int absinthe_make_periodic_ik(double* d_field, int X, int Y, int Z, int HX, int HY, int HZ,
                               void* stream);
 
+/* ---- multi-GPU halo exchange behind the boundary: j-slabs, one rank per GPU, P2P over NVLink -----------
+ *
+ * The reference reserves a node grid in the variant description -- TILING.NX/NY/NZ with index[] = {0,0,0}
+ * (ref template_tiling.cpp:189-203), per-group HALOS, and PUT / WAIT slots in the schedule
+ * (ref stencil_generator.py:23-37) -- and never fills them in.  Here: rank r of n owns the j-slab
+ * [r*Y, (r+1)*Y) of a periodic X x (n*Y) x Z domain.  Every rank creates an exchange *window* on its
+ * GPU (per group: double-buffered receive buffers for the rows of both neighbours, and arrival flags)
+ * and exports it as a 64-byte CUDA IPC handle; the host side passes the handles of ranks r-1 and r+1
+ * (mod n) to absinthe_comm_connect by whatever channel it has (torch.distributed, MPI, a file).
+ *
+ *   PUT  (absinthe_variant_put_group):  one kernel stores the first / last HY interior rows of all outputs
+ *        of the group -- every plane, full padded width, so i/k halos travel along -- straight into the
+ *        neighbours' windows through peer-mapped pointers and then raises their arrival flags.
+ *   WAIT (absinthe_variant_wait_group): one kernel waits for both neighbours' flags of the matching PUT
+ *        and copies the received rows into the low / high j-halo.
+ *
+ * No pack buffers, no collective library, two launches per group.  Enqueue the PUT after the group's
+ * kernel (any stream ordered after it) and the WAIT on the stream of the kernel that reads the halos --
+ * at the latest before the group's kernel runs again: a second PUT of a group without the WAIT of the
+ * first fails with -6.  With n = 1 both neighbours are the rank itself and PUT + WAIT equal the periodic
+ * update of the j faces. */
+#define ABSINTHE_COMM_HANDLE_BYTES 64
+int absinthe_comm_create(absinthe_variant* v, int rank, int nranks,
+                         unsigned char handle[ABSINTHE_COMM_HANDLE_BYTES]);
+int absinthe_comm_connect(absinthe_variant* v, const unsigned char* prev_handle,
+                          const unsigned char* next_handle);
+int absinthe_variant_put_group(absinthe_variant* v, int group, void* stream);
+int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream);
+int absinthe_comm_destroy(absinthe_variant* v);
+
 #ifdef __cplusplus
 }
 #endif

@@ -37,12 +37,12 @@ def field_seed(kernel, name):
     return sum(ord(c) * (n + 1) for n, c in enumerate(kernel + ":" + name)) % 100003
 
 
-def run_check(programs, world=1, rank=0, device=0, windows=None):
+def run_check(programs, world=1, rank=0, device=0, windows=None, exchange_kind="p2p"):
     """``programs``: [(kernel, program)] as ``bench.workload_programs()`` yields them.  Returns a report dict with
     ``ok`` and one entry per (kernel, window)."""
     import torch
     from absinthe_b200 import programs as P
-    from absinthe_b200.distributed import SlabExchange
+    from absinthe_b200.distributed import P2PExchange, SlabExchange
     from absinthe_b200.launcher import Variant
     from oracle.reference_oracle import Oracle
     report = {"ok": True, "rank": rank, "world": world, "windows": []}
@@ -56,7 +56,7 @@ def run_check(programs, world=1, rank=0, device=0, windows=None):
         ins = [global_field(field_seed(kernel, n), mine, extent, dev) for n in v.inputs]
         outs = [v.empty_field() for _ in v.outputs]
         v.bind(ins, outs)
-        exchange = SlabExchange(v, world, rank) if world > 1 else None
+        exchange = (P2PExchange if exchange_kind == "p2p" else SlabExchange)(v, world, rank) if world > 1 else None
         for g in range(1, v.n_groups + 1):                  # one step, as bench.py runs it
             if exchange is not None and g > 1:
                 exchange.wait(g - 1)

@@ -132,3 +132,71 @@ def test_bench_variants_match_the_oracle_across_two_slabs(launcher_lib):
     assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
     report = json.loads([line for line in proc.stdout.splitlines() if line.startswith("{")][-1])
     assert report["check"] == "ok" and report["n_gpus"] == 2 and not report["failed"]
+
+
+# ---- the exchange inside the launcher: P2P windows (absinthe_comm_*, put_group / wait_group) --------------
+def _global_oracle(kernel, slab, world):
+    from oracle.reference_oracle import Oracle
+    from absinthe_b200 import programs as P
+    from seam_check import field_seed, global_field
+    X, Y, Z = slab
+    extent = (X, world * Y, Z)
+    oracle = Oracle(P.make_program(kernel, domain=extent))
+    box = ((-3, X + 3), (-3, world * Y + 3), (-3, Z + 3))
+    inputs = [global_field(field_seed(kernel, n), box, extent, "cpu").numpy() for n in oracle.inputs]
+    return dict(zip(oracle.outputs, oracle.run(inputs)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel", ["diffusion", "fastwaves"])
+def test_p2p_exchange_on_one_rank_is_the_periodic_update(launcher_lib, kernel, tmp_path):
+    from p2p_worker import worker
+    slab = (48, 20, 10)
+    worker(0, 1, 29621, kernel, slab, 2, str(tmp_path / "r%d.npz"))
+    want = _global_oracle(kernel, slab, 1)
+    got = np.load(str(tmp_path / "r0.npz"))
+    for name, w in want.items():
+        assert np.array_equal(got[name], w), name
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kernel,world", [("diffusion", 2), ("fastwaves", 2), ("fastwaves", 3)])
+def test_p2p_exchange_between_processes(launcher_lib, kernel, world, tmp_path):
+    """Ranks are separate processes (CUDA IPC windows); they may share one GPU, so this runs on a 1-GPU box too."""
+    from p2p_worker import worker
+    slab = (48, 20, 10)
+    result = str(tmp_path / "r%d.npz")
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=worker, args=(r, world, 29622 + world, kernel, slab, 3, result)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(300)
+        assert p.exitcode == 0
+    want = _global_oracle(kernel, slab, world)
+    Y = slab[1]
+    for r in range(world):
+        got = np.load(result % r)
+        for name, w in want.items():
+            assert np.array_equal(got[name], w[:, r * Y:r * Y + Y + 6, :]), (name, r)
+
+
+@pytest.mark.gpu
+def test_second_put_without_wait_is_refused(launcher_lib):
+    from absinthe_b200 import programs as P
+    from absinthe_b200.distributed import P2PExchange
+    from absinthe_b200.launcher import LauncherError, Variant
+    v = Variant.from_program(P.make_program("advection", None, [(2, 2, 2)], domain=(40, 16, 8)))
+    v.bind([v.empty_field() for _ in v.inputs], [v.empty_field() for _ in v.outputs])
+    with pytest.raises(LauncherError, match="not connected"):
+        v.put_group(1)
+    exchange = P2PExchange(v, 1, 0)
+    v.apply_group(1, with_halo=False)
+    exchange.update_async(1)
+    with pytest.raises(LauncherError, match="has not been waited for"):
+        v.put_group(1)
+    exchange.wait(1)
+    exchange.wait(1)                                   # nothing outstanding: no-op
+    exchange.update(1)
+    torch.cuda.synchronize()
+    v.close()
