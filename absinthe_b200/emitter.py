@@ -682,8 +682,13 @@ class Plan:
         training = p.get("TRAINING", {})
         lines = ["absinthe-variant 1", "name %s" % (p.get("VARIANT") or p.get("NAME") or "variant"),
                  "# runs %d" % p.get("RUNS", 64), "# flush %d" % int(bool(p.get("FLUSH", True))),
-                 "# training %d" % int(bool(training))] + (["# verify 1"] if p.get("VERIFY") else []) + [
-                 "domain %d %d %d %d %d %d" % tuple(p[k] for k in ("X", "Y", "Z", "HX", "HY", "HZ"))]
+                 "# training %d" % int(bool(training)),
+                 # node grid of the variant description (ref template_tiling.cpp:189-203): ranks along j; the
+                 # domain line below is one rank's slab, "global" the decomposed extent
+                 "# nodes %d %d %d" % tuple(p["TILING"].get(k, 1) for k in ("NX", "NY", "NZ")),
+                 "# global %d %d %d" % tuple(p.get("GLOBAL", (p["X"], p["Y"], p["Z"])))]
+        lines += ["# verify 1"] if p.get("VERIFY") else []
+        lines.append("domain %d %d %d %d %d %d" % tuple(p[k] for k in ("X", "Y", "Z", "HX", "HY", "HZ")))
         for name in self.inputs:
             lines.append("field %s in" % name)
         for name in self.outputs:

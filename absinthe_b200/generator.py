@@ -73,6 +73,7 @@ def render(template, program):
     if template not in CUDA_TEMPLATES:
         raise ValueError("absinthe_b200 renders %s, not '%s' (the C++/OpenMP templates belong to the "
                          "reference)" % (" / ".join(CUDA_TEMPLATES), template))
+    decompose(program)
     A.analyse(program)
     if "SCHEDULE" not in program:
         compute_schedule(program)
@@ -83,6 +84,20 @@ def render(template, program):
     context["TRAINING"] = template == "template_training.cu"
     source = _environment().get_template(template).render(context)
     return source, plan.descriptor_text(), plan.nvcc_flags()
+
+
+def decompose(program):
+    """Apply the node grid ``TILING.NX/NY/NZ`` (ref template_tiling.cpp:189-203): the kernels of one rank work
+    on its subdomain.  The backend decomposes along j only (rows stay contiguous, k stays whole for the vertical
+    dependences): ``X, Y, Z`` become the slab, ``GLOBAL`` keeps the decomposed extent."""
+    tiling = program["TILING"]
+    nodes = tuple(tiling.get(k, 1) for k in ("NX", "NY", "NZ"))
+    if nodes == (1, 1, 1) or "GLOBAL" in program:
+        return
+    assert nodes[0] == 1 and nodes[2] == 1, "the B200 backend decomposes along j only (TILING.NX = TILING.NZ = 1)"
+    assert program["Y"] % nodes[1] == 0, "Y must be divisible by TILING.NY"
+    program["GLOBAL"] = (program["X"], program["Y"], program["Z"])
+    program["Y"] //= nodes[1]
 
 
 REFERENCE_SUFFIX = "_reference"
@@ -167,9 +182,15 @@ def generate_script(name, experiments, cores, runs):
         package_root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
         handle.write("export PYTHONPATH=%s:$PYTHONPATH\n\n" % package_root)
         # one interpreter start per repetition: the runner takes any number of variants and prints
-        # the same per-variant protocol as one process each would
+        # the same per-variant protocol as one process each would.  Experiments with a node grid
+        # (TILING.NY ranks along j) run under torchrun, one rank per GPU.
+        ranks = max([e.get("TILING", {}).get("NY", 1) for e in experiments.values()] or [1])
+        launch = "%s -m absinthe_b200.runner" % os.path.basename(sys.executable)
+        if ranks > 1:
+            launch = ("%s -m torch.distributed.run --nnodes=1 --nproc-per-node %d --master-addr 127.0.0.1 "
+                      "--master-port 29517 -m absinthe_b200.runner" % (os.path.basename(sys.executable), ranks))
         for _ in range(runs):
-            handle.write("%s -m absinthe_b200.runner \\\n" % os.path.basename(sys.executable))
+            handle.write(launch + " \\\n")
             handle.write(" \\\n".join("    ./" + key for key in experiments) + "\n")
 
 

@@ -89,6 +89,60 @@ def run_variant(stem, runs, flush=True, training=False, device=0, out=sys.stdout
     return np.array(total), np.array(halo)
 
 
+def run_variant_ranks(stem, runs, rank, world, flush=True, device=0, out=sys.stdout):
+    """The same protocol with the domain cut into ``world`` j-slabs, one rank (process) per GPU: the node grid of
+    the variant description (``# nodes`` in the descriptor; ref template_tiling.cpp:189-203) filled in.  After
+    every group the rank PUTs its edge rows into the neighbours' exchange windows (P2P over NVLink) and WAITs for
+    theirs before the next group (ref stencil_generator.py:23-37).  ``total`` is the slowest rank's time per run,
+    ``halo`` the part of it not spent in the group kernels.  Rank 0 prints."""
+    import torch
+    import torch.distributed as dist
+    from .distributed import P2PExchange
+    from .fields import slab_field
+    from .launcher import Variant, flush_l2
+    variant = Variant(stem + ".desc", stem + ".cubin", device)
+    name = open(stem + ".desc").read().split("\n")[1].split(" ", 1)[1]
+    say = (lambda *a: print(*a, file=out)) if rank == 0 else (lambda *a: None)
+    say("-> configuration")
+    say("   - variant " + name)
+    say("   - domain %d, %d, %d" % (variant.X, variant.Y * world, variant.Z))
+    say("   - runs %d" % runs)
+    say("   - ranks %d (j-slabs of %d rows, P2P halo exchange)" % (world, variant.Y))
+    slab, halo = (variant.X, variant.Y, variant.Z), (variant.HX, variant.HY, variant.HZ)
+    inputs = [slab_field(name, n, slab, halo, rank, world, "cuda:%d" % device) for n in variant.inputs]
+    outputs = [variant.empty_field() for _ in variant.outputs]
+    variant.bind(inputs, outputs)
+    exchange = P2PExchange(variant, world, rank)
+    groups = range(1, variant.n_groups + 1)
+    for run in range(2 * runs):
+        if flush:
+            flush_l2()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(2 + 2 * variant.n_groups)]
+        marks[0].record()
+        for g in groups:
+            if g > 1:
+                exchange.wait(g - 1)                 # WAIT: this group reads the halos of the previous one
+            marks[2 * g - 1].record()
+            variant.apply_group(g, with_halo=False)
+            marks[2 * g].record()
+            exchange.update_async(g)                 # PUT, overlapped with the next kernel
+        for g in groups:
+            exchange.wait(g)
+        marks[-1].record()
+        torch.cuda.synchronize(device)
+        if run % 2 == 1:
+            total = marks[0].elapsed_time(marks[-1])
+            kernels = sum(marks[2 * g - 1].elapsed_time(marks[2 * g]) for g in groups)
+            times = torch.tensor([total, total - kernels], dtype=torch.float64)
+            dist.all_reduce(times, op=dist.ReduceOp.MAX)
+            say("-> apply stencils...")
+            say("   - total time (min/median/max) [ms]: %g" % times[0].item())
+            say("   - halo time (min/median/max) [ms]: %g" % times[1].item())
+    dist.barrier()
+    variant.close()
+    return outputs
+
+
 def main(argv=None):
     parser = argparse.ArgumentParser(description=__doc__.split("\n")[0])
     parser.add_argument("stem", nargs="+", help="path(s) of the variant(s) without extension")
@@ -96,6 +150,15 @@ def main(argv=None):
     parser.add_argument("--no-flush", action="store_true")
     parser.add_argument("--device", type=int, default=0)
     args = parser.parse_args(argv)
+    import os
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if world > 1:                                    # launched by torchrun: one rank per GPU (ranks share GPUs if fewer)
+        import torch
+        import torch.distributed as dist
+        dist.init_process_group("gloo")              # host-side channel for the IPC handles and the timing maxima
+        args.device = int(os.environ.get("LOCAL_RANK", "0")) % torch.cuda.device_count()
+        torch.cuda.set_device(args.device)
     for stem in args.stem:
         meta = {}
         with open(stem + ".desc") as handle:
@@ -106,9 +169,21 @@ def main(argv=None):
         runs = args.runs or int(meta.get("runs", 64))
         flush = not args.no_flush and meta.get("flush", "1") == "1"
         training = meta.get("training", "0") == "1"
-        run_variant(stem, runs, flush=flush, training=training, device=args.device,
-                    verify=meta.get("verify", "0") == "1")
+        nodes = [int(t) for t in meta.get("nodes", "1 1 1").split()]
+        if world > 1:
+            if nodes[1] != world:
+                raise SystemExit("%s is generated for TILING.NY = %d ranks, launched with %d" % (stem, nodes[1], world))
+            run_variant_ranks(stem, runs, rank, world, flush=flush, device=args.device)
+        else:
+            if nodes[1] != 1:
+                raise SystemExit("%s is decomposed into %d j-slabs: launch it with torchrun --nproc-per-node %d "
+                                 "(run.sh does)" % (stem, nodes[1], nodes[1]))
+            run_variant(stem, runs, flush=flush, training=training, device=args.device,
+                        verify=meta.get("verify", "0") == "1")
         sys.stdout.flush()
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":

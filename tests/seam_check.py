@@ -16,25 +16,7 @@ WINDOW = (40, 28, 14)
 H = 3
 
 
-def hashed(gi, gj, gk, seed):
-    """Exact pseudo-random doubles in [0.5, 1.5) from integer coordinates (torch int64 tensors, broadcast)."""
-    v = (gi * 73856093) ^ (gj * 19349663) ^ (gk * 83492791) ^ (seed * 2654435761)
-    v = (v ^ (v >> 13)) * 1274126177
-    return ((v ^ (v >> 16)) & 0xFFFFF).double() / float(1 << 20) + 0.5
-
-
-def global_field(seed, box, extent, device):
-    """Padded field over the global index box ``(i0, i1), (j0, j1), (k0, k1)`` of a periodic ``extent`` domain."""
-    import torch
-    (i0, i1), (j0, j1), (k0, k1) = box
-    gi = torch.arange(i0, i1, device=device, dtype=torch.int64) % extent[0]
-    gj = torch.arange(j0, j1, device=device, dtype=torch.int64) % extent[1]
-    gk = torch.arange(k0, k1, device=device, dtype=torch.int64) % extent[2]
-    return hashed(gi[None, None, :], gj[None, :, None], gk[:, None, None], seed).contiguous()
-
-
-def field_seed(kernel, name):
-    return sum(ord(c) * (n + 1) for n, c in enumerate(kernel + ":" + name)) % 100003
+from absinthe_b200.fields import field_seed, global_field  # noqa: E402,F401  (re-exported for the tests)
 
 
 def run_check(programs, world=1, rank=0, device=0, windows=None, exchange_kind="p2p"):

@@ -131,3 +131,21 @@ def test_verify_emits_the_sequential_reference_variant(tmp_path):
     makefile = (tmp_path / "Makefile").read_text()
     assert "all: fw.cubin fw_reference.cubin plain.cubin\n" in makefile
     assert "fw_reference.cubin: fw_reference.cu\n" in makefile and "plain_reference" not in makefile
+
+
+def test_node_grid_decomposes_along_j(tmp_path):
+    """TILING.NY ranks (ref template_tiling.cpp:189-203): kernels are generated for one rank's slab, the descriptor
+    records the node grid, run.sh launches one rank per GPU."""
+    program = P.make_program("fastwaves", variant="fw2", domain=(64, 64, 20))
+    program["TILING"]["NY"] = 2
+    G.generate_code("template_tiling.cu", str(tmp_path / "fw2.cu"), program)
+    desc = (tmp_path / "fw2.desc").read_text()
+    assert "# nodes 1 2 1" in desc and "# global 64 64 20" in desc and "domain 64 32 20 3 3 3" in desc
+    assert "constexpr int X = 64, Y = 32, Z = 20;" in (tmp_path / "fw2.cu").read_text()
+    G.generate_script(str(tmp_path / "run.sh"), {"fw2": program}, 148, 1)
+    script = (tmp_path / "run.sh").read_text()
+    assert "torch.distributed.run --nnodes=1 --nproc-per-node 2" in script and "-m absinthe_b200.runner" in script
+    bad = P.make_program("fastwaves", variant="fw3", domain=(64, 64, 20))
+    bad["TILING"]["NX"] = 2
+    with pytest.raises(AssertionError, match="along j only"):
+        G.generate_code("template_tiling.cu", str(tmp_path / "fw3.cu"), bad)

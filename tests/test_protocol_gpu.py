@@ -90,3 +90,30 @@ def test_compare_fields_counts_like_the_reference(launcher_lib):
     b[3 + 4, 3 + 5, 3 + 19] = float("nan")        # NaN never compares greater: a match, as in the reference
     assert compare_fields(a, b, dims) == (1, 20 * 6 * 5 - 1)
     assert compare_fields(a, b, dims, tolerance=1e-8) == (2, 20 * 6 * 5 - 2)
+
+
+def test_runner_drives_two_ranks(launcher_lib, tmp_path):
+    """``run.sh`` of a program with TILING.NY = 2: torchrun, one process per rank (they may share a GPU), P2P halo
+    exchange inside the launcher; rank 0 prints the reference's protocol and parse_results reads it."""
+    import subprocess
+    import sys
+    from absinthe_b200 import generator as G
+    program = P.make_program("fastwaves", variant="fw-2ranks", domain=(64, 48, 12), RUNS=3)
+    program["TILING"]["NY"] = 2
+    program["CUDA"] = {"INLINE": "all", "FUSE_HALO": True}
+    stem = str(tmp_path / "fw-2ranks")
+    flags = P.clone(program)
+    G.generate_code("template_tiling.cu", stem + ".cu", flags)
+    subprocess.check_call(G.nvcc_command(flags["CUDA"]["NVCC_FLAGS"], stem + ".cu", stem + ".cubin"))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
+           "127.0.0.1", "--master-port", "29631", "-m", "absinthe_b200.runner", stem]
+    import os
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    proc = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=root,
+                          env=dict(os.environ, PYTHONPATH=root))
+    assert proc.returncode == 0, proc.stdout[-2000:] + proc.stderr[-3000:]
+    log = tmp_path / "log.txt"
+    log.write_text(proc.stdout)
+    rows = G.parse_results(str(log), 0)
+    assert len(rows) == 3 and rows[0][0] == "fw-2ranks" and rows[0][1:4] == ["64", "48", "12"]
+    assert all(float(r[4]) >= float(r[5]) >= 0 for r in rows)
