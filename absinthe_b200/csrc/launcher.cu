@@ -396,7 +396,7 @@ struct Group {
 };
 
 // interior comparison of the reference's verifier (ref template_tiling.cpp:383-392): a point is an error
-// when |expected - actual| > max(|expected|, |actual|) * tolerance (so NaN never counts as one)
+// when |expected - actual| > max(|expected|, |actual|) * tolerance, or when it is not finite although expected is
 __global__ void compare_kernel(const double* __restrict__ expected, const double* __restrict__ actual,
                                Geometry g, double tolerance, unsigned long long* counters) {
     const long cells = (long)g.X * g.Y * g.Z;
@@ -405,7 +405,9 @@ __global__ void compare_kernel(const double* __restrict__ expected, const double
         const long i = n % g.X, j = (n / g.X) % g.Y, k = n / ((long)g.X * g.Y);
         const long at = (i + g.HX) + (j + g.HY) * g.row() + (k + g.HZ) * g.plane();
         const double e = expected[at], a = actual[at];
-        if (fabs(e - a) > fmax(fabs(e), fabs(a)) * tolerance) ++errors;
+        // the reference's test never fires on NaN (every comparison with NaN is false, ref :386): a variant
+        // that returns NaN or inf where the reference is finite must not pass as "0 errors"
+        if (fabs(e - a) > fmax(fabs(e), fabs(a)) * tolerance || (isfinite(e) && !isfinite(a))) ++errors;
         else ++matches;
     }
     for (int d = 16; d > 0; d >>= 1) {

@@ -111,7 +111,7 @@ def test_verify_emits_the_sequential_reference_variant(tmp_path):
     assert [g["GROUPS"][0]["STENCILS"] for g in ref["TILING"]["GROUPS"]] == [[name] for name in sequence]
     assert all((g["GROUPS"][0]["NX"], g["GROUPS"][0]["NY"], g["GROUPS"][0]["NZ"]) == (1, 8, 15)
                for g in ref["TILING"]["GROUPS"])
-    assert ref["OUTPUTS"] == program["OUTPUTS"] and ref["VERIFY"] is False and "CUDA" not in ref
+    assert ref["OUTPUTS"] == program["OUTPUTS"] and ref["VERIFY"] is False and ref["CUDA"] == {"LOAD": "ldg", "FMAD": False}
     assert ref["VARIANT"] == "fastwaves-split_reference"
 
     G.generate_code("template_tiling.cu", str(tmp_path / "fw.cu"), program)
@@ -149,3 +149,22 @@ def test_node_grid_decomposes_along_j(tmp_path):
     bad["TILING"]["NX"] = 2
     with pytest.raises(AssertionError, match="along j only"):
         G.generate_code("template_tiling.cu", str(tmp_path / "fw3.cu"), bad)
+
+
+def test_makefile_flags_are_per_target(tmp_path):
+    strict = P.make_program("advection", variant="strict")
+    relaxed = P.make_program("advection", variant="relaxed")
+    relaxed["CUDA"] = {"FMAD": True}
+    G.generate_makefile(str(tmp_path / "Makefile"), {"strict": strict, "relaxed": relaxed})
+    rules = (tmp_path / "Makefile").read_text().split("\n\n")
+    rule = {r.split(".cubin:")[0]: r for r in rules if ".cubin:" in r}
+    assert "$(STRICT)" in rule["strict"] and "$(STRICT)" not in rule["relaxed"]
+
+
+def test_verify_reference_uses_the_plain_kernels():
+    program = P.make_program("fastwaves", variant="v", VERIFY=True)
+    program["CUDA"] = {"INLINE": "all", "SHUFFLE": True, "FUSE_HALO": True, "FMAD": True}
+    from absinthe_b200 import analysis as A
+    A.analyse(program)
+    ref = G.sequential_reference(program)
+    assert ref["CUDA"] == {"LOAD": "ldg", "FMAD": False} and len(ref["TILING"]["GROUPS"]) == 9
