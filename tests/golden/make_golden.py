@@ -11,6 +11,7 @@ fixtures it writes are small and committed, so the tests that use them run anywh
                                  (srand(0)/rand(), periodic) and of the outputs its own
                                  ``compute_reference`` computes from them, strict IEEE build
 * ``parse_results.json``         rows the reference's ``parse_results`` extracts from a sample log
+* ``training_digests.json``     the same for four fitcache / fitddr training programs
 * ``shipped_medians.json``       estimate and median measurement of every variant the reference ships
                                  results for (``*/estimates.csv`` joined with ``*/results.csv``)
 """
@@ -125,6 +126,35 @@ def reference_digests():
     return out
 
 
+TRAINING_CASES = [("fitcache", "PT12", (10, 3, 4)), ("fitcache", "PT20", (10, 2, 5)), ("fitddr", "IN2BD1", (10, 3, 4)),
+                  ("fitddr", "IN3BD2", (20, 2, 3))]
+
+
+def training_digests():
+    """Reference-computed values for training programs: the program of fitcache.py / fitddr.py (all nine stencils of a
+    variant, 2 x 2 x 5*CORES tiles) rendered by the reference's generator with template_tiling.cpp, whose
+    compute_reference evaluates the same stencils sequentially over the whole domain, strict flags."""
+    import numpy as np
+    from absinthe_b200 import programs as P
+    from oracle import build_ref
+
+    def sha(a):
+        return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+    out = {}
+    for family, variant, shape in TRAINING_CASES:
+        program = P.training_program(family, variant, shape, cores=2, stride=20)
+        program.pop("TRAINING")
+        name = "%s-%s-%s" % (family, variant, "x".join(map(str, shape)))
+        dump = build_ref.build_dump(program, "golden_" + name.replace("-", "_"))
+        inputs = dump.fill_inputs()
+        outputs = dump.compute(inputs)
+        out[name] = {"input_order": dump.inputs, "inputs": {k: sha(v) for k, v in inputs.items()},
+                     "outputs": {k: sha(v) for k, v in outputs.items()},
+                     "abs_max": {k: float(np.abs(v).max()) for k, v in outputs.items()}}
+        print("digest", name)
+    return out
+
+
 SAMPLE_LOG = """-> configuration
    - variant alpha
    - domain 64, 64, 60
@@ -191,7 +221,7 @@ def main():
     for name, fn in (("stencil_fingerprints", stencil_fingerprints), ("analysis", analysis_fixtures),
                      ("parse_results", parse_fixture), ("shipped_variants", shipped_variants),
                      ("shipped_medians", shipped_medians),
-                     ("reference_digests", reference_digests)):
+                     ("reference_digests", reference_digests), ("training_digests", training_digests)):
         with open(os.path.join(GOLDEN, name + ".json"), "w") as handle:
             json.dump(fn(), handle, indent=1, sort_keys=True)
         print("wrote", name)

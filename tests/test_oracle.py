@@ -62,3 +62,27 @@ def test_oracle_against_live_reference():
     got = oracle.run([inputs[n] for n in oracle.inputs])
     for field, array in zip(oracle.outputs, got):
         assert array.tobytes() == want[field].tobytes()
+
+
+TRAINING = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "training_digests.json")))
+
+
+@pytest.mark.parametrize("name", sorted(TRAINING))
+def test_oracle_reproduces_reference_digests_of_training_programs(name):
+    """fitcache / fitddr stencils (ref fitcache.py:16-58, fitddr.py:16-124): values computed by the reference's own
+    compute_reference for the training programs' stencils (tests/golden/make_golden.py: training_digests)."""
+    family, variant, shape = name.split("-")
+    program = P.training_program(family, variant, tuple(int(v) for v in shape.split("x")), cores=2, stride=20)
+    gold = TRAINING[name]
+    oracle = Oracle(P.clone(program))
+    assert sorted(oracle.inputs) == sorted(gold["input_order"])
+    fields = oracle.empty_fields(len(gold["input_order"]))
+    oracle.lib.oracle_fill_inputs(oracle._pointers(fields), len(fields), 0)
+    by_name = dict(zip(gold["input_order"], fields))
+    for field, want in gold["inputs"].items():
+        assert digest(by_name[field]) == want
+    outputs = oracle.run([by_name[n] for n in oracle.inputs])
+    assert sorted(oracle.outputs) == sorted(gold["outputs"])
+    for field, array in zip(oracle.outputs, outputs):
+        assert digest(array) == gold["outputs"][field], "output %s differs from compute_reference" % field
+        assert float(np.abs(array).max()) == gold["abs_max"][field]
