@@ -53,6 +53,13 @@ def applicable(program, group, opts):
     return opts.get("LOAD", "tma") == "tma" and row % 2 == 0 and bool(group["INPUTS"])
 
 
+def k_dependent(group):
+    """True when a stencil of the group reads another stencil of the group at a k-offset: the case in which the
+    classic kernel evaluates intermediates on k-extended boxes (or re-evaluates them per plane)."""
+    names = {s["NAME"] for s in group["STENCILS"]}
+    return any(box[2] != (0, 0) for s in group["STENCILS"] for f, box in s["OFFSETS"].items() if f in names)
+
+
 class ColumnPlan:
     """Everything needed to render and launch the column kernel of one fused group."""
 

@@ -59,7 +59,8 @@ DEFAULTS = {
     "L2_PREFETCH": 0,            # work items whose boxes are prefetched into L2 ahead of the ring
     "STREAM_K": False,           # True: walk a tile column plane by plane through rings of k-planes in shared
                                  # memory; "regs": column kernel (column.py) -- a thread owns a column, values
-                                 # wanted again at lower planes are carried in registers, no CTA barriers
+                                 # wanted again at lower planes are carried in registers, no CTA barriers;
+                                 # "auto": column kernel for groups whose stencils read each other across k
     "COLUMN": None,              # column kernel shape: {"WARPS": (WX, WY), "PLANES": planes per TMA box, "SLOTS": ring}
     "PREFETCH": 2,               # STREAM_K: input planes in flight beyond the ones being read
 }
@@ -642,7 +643,10 @@ class Plan:
                 opts = self._group_options(inner["ID"] + 1)
                 # kernels carry the sequence's name so that launch lists attribute them (absinthe_<name>_g<id>)
                 symbol = "absinthe_%s_g%d" % (re.sub(r"\W", "_", str(program.get("NAME", "variant"))), inner["ID"] + 1)
-                if opts["STREAM_K"] == "regs" and column.applicable(program, inner, opts):
+                wanted = opts["STREAM_K"] == "regs" or (opts["STREAM_K"] == "auto" and column.k_dependent(inner))
+                if opts["STREAM_K"] == "auto" and not wanted:
+                    opts = dict(opts, STREAM_K=False)
+                if wanted and column.applicable(program, inner, opts):
                     self.groups.append(column.ColumnPlan(program, inner, opts, symbol))
                 else:
                     self.groups.append(GroupPlan(program, inner, opts, symbol))

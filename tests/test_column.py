@@ -83,3 +83,15 @@ def test_column_kernel_compiles_for_sm_100a(tmp_path, cuda):
     sass = subprocess.run(["cuobjdump", "-sass", str(tmp_path / "column.cubin")], capture_output=True, text=True).stdout
     assert "UTMALDG" in sass and "SHFL" in sass and "BAR.SYNC" in sass
     assert sass.count("BAR.SYNC") == 1                    # only the start-up barrier: no CTA barrier in the k-loop
+
+
+def test_auto_picks_column_kernels_for_k_dependent_groups_only():
+    q = P.make_program("fastwaves", [F[:4], F[4:6], F[6:]], [(2, 4, 3), (1, 8, 2), (4, 2, 6)])
+    q["CUDA"] = {"STREAM_K": "auto", "INLINE": "all"}
+    groups = Plan(q).groups
+    assert [g.column for g in groups] == [True, False, True]      # ppgc reads ppgk(k+1); div reads udc(k+1)
+    assert not groups[1].stream and groups[1].inlined == set()    # the classic kernel, not the plane-ring one
+    d = P.KERNELS["diffusion"][1]()
+    q = P.make_program("diffusion", [d], [(2, 4, 3)])
+    q["CUDA"] = {"STREAM_K": "auto"}
+    assert [g.column for g in Plan(q).groups] == [False]

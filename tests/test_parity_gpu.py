@@ -42,6 +42,7 @@ OPTIONS = [
     ("poll-warp", {"INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "POLL_WARP": True, "STAGES": 3}),
     ("poll-warp-generic", {"POLL_WARP": True, "THREADS": 128}),
     ("column", {"STREAM_K": "regs"}),
+    ("column-auto", {"STREAM_K": "auto", "INLINE": "all", "BLOCK": (2, 1), "SHUFFLE": True, "FUSE_HALO": True}),
     ("column-rj2-planes2-halo", {"STREAM_K": "regs", "BLOCK": (2, 1), "COLUMN": {"WARPS": (1, 2), "PLANES": 2},
                                  "FUSE_HALO": True}),
     ("column-rj3-planes3", {"STREAM_K": "regs", "BLOCK": (3, 1),

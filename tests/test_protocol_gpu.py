@@ -87,9 +87,15 @@ def test_compare_fields_counts_like_the_reference(launcher_lib):
     b[3 + 2, 3 + 1, 3 + 7] *= 1.0 + 3e-7          # beyond the 1e-7 relative tolerance
     b[3 + 0, 3 + 0, 3 + 0] *= 1.0 + 5e-8          # within it
     b[0, 0, 0] = 99.0                             # halo: not looked at
-    b[3 + 4, 3 + 5, 3 + 19] = float("nan")        # NaN never compares greater: a match, as in the reference
     assert compare_fields(a, b, dims) == (1, 20 * 6 * 5 - 1)
     assert compare_fields(a, b, dims, tolerance=1e-8) == (2, 20 * 6 * 5 - 2)
+    # the reference's test never fires on NaN (ref template_tiling.cpp:386), so an all-NaN output would verify as
+    # "0 errors"; here a non-finite value where the expected one is finite is an error
+    b[3 + 4, 3 + 5, 3 + 19] = float("nan")
+    b[3 + 4, 3 + 5, 3 + 18] = float("inf")
+    assert compare_fields(a, b, dims) == (3, 20 * 6 * 5 - 3)
+    a[3 + 4, 3 + 5, 3 + 19] = float("nan")        # expected NaN as well: not this check's business
+    assert compare_fields(a, b, dims) == (2, 20 * 6 * 5 - 2)
 
 
 def test_runner_drives_two_ranks(launcher_lib, tmp_path):
