@@ -61,6 +61,9 @@ struct Driver {
                                      const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill) = nullptr;
     CUresult (*GetErrorString)(CUresult, const char**) = nullptr;
+    // stream memory operations (optional: the exchange falls back to kernels without them)
+    CUresult (*StreamWaitValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned) = nullptr;
+    CUresult (*StreamWriteValue64)(CUstream, CUdeviceptr, cuuint64_t, unsigned) = nullptr;
     bool ready = false;
 };
 Driver g_drv;
@@ -87,6 +90,9 @@ int driver_resolve_all() {
     if ((rc = resolve("cuLaunchKernel", g_drv.LaunchKernel))) return rc;
     if ((rc = resolve("cuTensorMapEncodeTiled", g_drv.TensorMapEncodeTiled))) return rc;
     if ((rc = resolve("cuGetErrorString", g_drv.GetErrorString))) return rc;
+    if (resolve("cuStreamWaitValue64", g_drv.StreamWaitValue64) || resolve("cuStreamWriteValue64", g_drv.StreamWriteValue64))
+        g_drv.StreamWaitValue64 = nullptr, g_drv.StreamWriteValue64 = nullptr;
+    g_error.clear();
     return 0;
 }
 
@@ -277,25 +283,37 @@ __device__ __forceinline__ void store_flag(unsigned long long* p, unsigned long 
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// The exchange kernels are built to squeeze in beside a compute kernel: 128 threads, one row per block pass,
+// 16-byte accesses, no 64-bit divisions (a fused group kernel can leave less than 4000 registers per SM free).
+constexpr int kExchangeThreads = 128;
+
+// rows [j0, j0+HY) of plane k of field f <-> buffer[((f * planes + k) * HY + r) * row ...]
+__device__ __forceinline__ void move_rows(FieldList fields, const Geometry& g, double* buffer, int j0, bool to_buffer) {
+    const int row = (int)g.row(), planes = (int)g.planes();
+    const long plane = g.plane();
+    const int lines = fields.count * planes * g.HY;
+    for (int line = blockIdx.x; line < lines; line += gridDim.x) {
+        const int r = line % g.HY, k = (line / g.HY) % planes, f = line / (g.HY * planes);
+        double* field = fields.ptr[f] + k * plane + (long)(j0 + r) * row;
+        double* dense = buffer + (long)line * row;
+        if ((row & 1) == 0) {                                   // even rows: both sides are 16-byte aligned
+            double2* a = reinterpret_cast<double2*>(to_buffer ? dense : field);
+            const double2* b = reinterpret_cast<const double2*>(to_buffer ? field : dense);
+            for (int i = threadIdx.x; i < row / 2; i += blockDim.x) a[i] = b[i];
+        } else {
+            for (int i = threadIdx.x; i < row; i += blockDim.x) (to_buffer ? dense : field)[i] = (to_buffer ? field : dense)[i];
+        }
+    }
+}
+
 // PUT: the first HY interior rows of every field go to the previous rank's "from next" buffer, the last HY
 // interior rows to the next rank's "from previous" buffer ([field][plane][HY][row], through peer-mapped
 // pointers); the last block to finish raises both arrival flags to `epoch`.
-__global__ void put_kernel(FieldList fields, Geometry g, double* __restrict__ to_prev, double* __restrict__ to_next,
-                           unsigned long long* flag_at_prev, unsigned long long* flag_at_next, unsigned* done,
-                           unsigned long long epoch) {
-    const long row = g.row(), plane = g.plane();
-    const long per_field = g.planes() * g.HY * row;
-    const long total = 2 * fields.count * per_field;
-    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < total; n += (long)gridDim.x * blockDim.x) {
-        const int side = (int)(n / (fields.count * per_field));
-        const long m = n % (fields.count * per_field);
-        const int f = (int)(m / per_field);
-        const long r = m % per_field;
-        const long k = r / (g.HY * row), q = r % (g.HY * row);
-        const long j0 = side ? g.Y : g.HY;                 // last / first HY interior rows (padded row index)
-        const double v = fields.ptr[f][k * plane + (j0 + q / row) * row + q % row];
-        (side ? to_next : to_prev)[m] = v;
-    }
+__global__ void __launch_bounds__(kExchangeThreads)
+put_kernel(FieldList fields, Geometry g, double* to_prev, double* to_next, unsigned long long* flag_at_prev,
+           unsigned long long* flag_at_next, unsigned* done, unsigned long long epoch) {
+    move_rows(fields, g, to_prev, g.HY, true);
+    move_rows(fields, g, to_next, g.Y, true);
     __threadfence_system();                                 // this thread's remote stores are out
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -308,31 +326,27 @@ __global__ void put_kernel(FieldList fields, Geometry g, double* __restrict__ to
     }
 }
 
-// WAIT: spin (bounded) until both neighbours have raised this rank's flags to `epoch`, then copy the rows they
-// stored into the low / high j-halo.
-__global__ void wait_kernel(FieldList fields, Geometry g, const double* __restrict__ from_prev,
-                            const double* __restrict__ from_next, const unsigned long long* flags,
-                            unsigned long long epoch) {
-    if (threadIdx.x == 0) {
-        unsigned long long spins = 0;
-        while (load_flag(flags) < epoch || load_flag(flags + 1) < epoch) {
-            __nanosleep(200);
-            if (++spins > (1ull << 24)) __trap();           // a neighbour that never arrives ends in an error, not a hang
-        }
+// raise flags from a kernel (copy-engine PUT on a driver without stream memory operations)
+__global__ void signal_kernel(unsigned long long* flag_at_prev, unsigned long long* flag_at_next, unsigned long long epoch) {
+    __threadfence_system();
+    store_flag(flag_at_prev, epoch);
+    store_flag(flag_at_next, epoch);
+}
+
+// spin (bounded) until both neighbours have raised this rank's flags to `epoch`
+__global__ void await_kernel(const unsigned long long* flags, unsigned long long epoch) {
+    unsigned long long spins = 0;
+    while (load_flag(flags) < epoch || load_flag(flags + 1) < epoch) {
+        __nanosleep(200);
+        if (++spins > (1ull << 24)) __trap();               // a neighbour that never arrives ends in an error, not a hang
     }
-    __syncthreads();
-    const long row = g.row(), plane = g.plane();
-    const long per_field = g.planes() * g.HY * row;
-    const long total = 2 * fields.count * per_field;
-    for (long n = blockIdx.x * (long)blockDim.x + threadIdx.x; n < total; n += (long)gridDim.x * blockDim.x) {
-        const int side = (int)(n / (fields.count * per_field));
-        const long m = n % (fields.count * per_field);
-        const int f = (int)(m / per_field);
-        const long r = m % per_field;
-        const long k = r / (g.HY * row), q = r % (g.HY * row);
-        const long j0 = side ? g.Y + g.HY : 0;              // high / low halo rows
-        fields.ptr[f][k * plane + (j0 + q / row) * row + q % row] = (side ? from_next : from_prev)[m];
-    }
+}
+
+// the rows the neighbours stored -> low / high j-halo
+__global__ void __launch_bounds__(kExchangeThreads)
+unpack_kernel(FieldList fields, Geometry g, double* from_prev, double* from_next) {
+    move_rows(fields, g, from_prev, 0, false);
+    move_rows(fields, g, from_next, g.Y + g.HY, false);
 }
 
 int launch_grid(long items, int threads) {
@@ -447,6 +461,7 @@ struct absinthe_variant {
         size_t data = 0;                         // offset (doubles) of [parity][from_prev | from_next] buffers
         size_t flags = 0;                        // offset (doubles) of {from_prev, from_next} arrival epochs
         unsigned long long put = 0, waited = 0;  // PUTs enqueued / WAITs enqueued
+        int engine = 0;                          // engine of the outstanding PUT
         cudaEvent_t unpacked = nullptr;          // recorded after the WAIT kernel of the latest epoch
     };
     int comm_rank = 0, comm_ranks = 0;
@@ -456,6 +471,7 @@ struct absinthe_variant {
     double* window_next = nullptr;
     bool prev_mapped = false, next_mapped = false;
     unsigned* put_done = nullptr;                // block counter of the PUT kernels (one per group)
+    cudaStream_t unpack_stream = nullptr;        // WAITs run here; the caller's stream waits for their event
     std::vector<CommGroup> comm_groups;
 };
 
@@ -1217,6 +1233,7 @@ int absinthe_comm_create(absinthe_variant* v, int rank, int nranks, unsigned cha
     RT(cudaMalloc(&v->put_done, sizeof(unsigned) * std::max<size_t>(v->comm_groups.size(), 1)));
     RT(cudaMemset(v->put_done, 0, sizeof(unsigned) * std::max<size_t>(v->comm_groups.size(), 1)));
     for (auto& c : v->comm_groups) RT(cudaEventCreateWithFlags(&c.unpacked, cudaEventDisableTiming));
+    RT(cudaStreamCreateWithFlags(&v->unpack_stream, cudaStreamNonBlocking));
     RT(cudaDeviceSynchronize());
     cudaIpcMemHandle_t h;
     RT(cudaIpcGetMemHandle(&h, v->window));
@@ -1261,6 +1278,8 @@ int absinthe_comm_destroy(absinthe_variant* v) {
     if (v->next_mapped && v->window_next) cudaIpcCloseMemHandle(v->window_next);
     for (auto& c : v->comm_groups)
         if (c.unpacked) cudaEventDestroy(c.unpacked);
+    if (v->unpack_stream) cudaStreamDestroy(v->unpack_stream);
+    v->unpack_stream = nullptr;
     if (v->window) cudaFree(v->window);
     if (v->put_done) cudaFree(v->put_done);
     v->window = v->window_prev = v->window_next = nullptr;
@@ -1287,7 +1306,24 @@ static int comm_group(absinthe_variant* v, int group, absinthe_variant::CommGrou
     return 0;                                             // a group without outputs has nothing to exchange
 }
 
-int absinthe_variant_put_group(absinthe_variant* v, int group, void* stream) {
+// strided rows <-> dense buffer with the copy engines: per field one 2-D copy (HY contiguous rows per plane)
+static int copy_rows(absinthe_variant* v, const Group& g, double* buffer, long j0, bool to_buffer, cudaStream_t s) {
+    const Geometry& q = v->geo;
+    const size_t width = (size_t)q.HY * q.row() * sizeof(double);
+    for (size_t n = 0; n < g.halo_fields.size(); ++n) {
+        double* field = v->fields[g.halo_fields[n]].ptr + j0 * q.row();
+        double* dense = buffer + n * (size_t)q.planes() * q.HY * q.row();
+        if (to_buffer)
+            RT(cudaMemcpy2DAsync(dense, width, field, (size_t)q.plane() * sizeof(double), width, (size_t)q.planes(),
+                                 cudaMemcpyDefault, s));
+        else
+            RT(cudaMemcpy2DAsync(field, (size_t)q.plane() * sizeof(double), dense, width, width, (size_t)q.planes(),
+                                 cudaMemcpyDefault, s));
+    }
+    return 0;
+}
+
+int absinthe_variant_put_group(absinthe_variant* v, int group, int engine, void* stream) {
     absinthe_variant::CommGroup* c = nullptr;
     Group* g = nullptr;
     size_t index = 0;
@@ -1295,6 +1331,7 @@ int absinthe_variant_put_group(absinthe_variant* v, int group, void* stream) {
     if (rc || !c) return rc;
     OnDevice on(v->device);
     if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
+    if (engine != ABSINTHE_PUT_KERNEL && engine != ABSINTHE_PUT_COPY) return fail(-3, "unknown PUT engine %d", engine);
     if (c->put != c->waited)
         return fail(-6, "group %d: the previous PUT has not been waited for (absinthe_variant_wait_group)", group);
     cudaStream_t s = (cudaStream_t)stream;
@@ -1310,6 +1347,7 @@ int absinthe_variant_put_group(absinthe_variant* v, int group, void* stream) {
     // the neighbours may only overwrite the buffers of this parity once this rank has unpacked them
     if (c->waited >= 1) RT(cudaStreamWaitEvent(s, c->unpacked, 0));
     const unsigned long long epoch = ++c->put;
+    c->engine = engine;
     const size_t slot = (c->face_doubles + 15) / 16 * 16;
     const size_t parity = (size_t)(epoch & 1);
     // my low rows -> previous rank's "from next" buffer; my high rows -> next rank's "from previous" buffer
@@ -1317,9 +1355,22 @@ int absinthe_variant_put_group(absinthe_variant* v, int group, void* stream) {
     double* to_next = v->window_next + c->data + (2 * parity + 0) * slot;
     unsigned long long* flag_at_prev = (unsigned long long*)(v->window_prev + c->flags) + 1;
     unsigned long long* flag_at_next = (unsigned long long*)(v->window_next + c->flags) + 0;
-    long total = 2L * list.count * q.planes() * q.HY * q.row();
-    int blocks = std::min(launch_grid(total, 256), sm_count() * 2);
-    put_kernel<<<blocks, 256, 0, s>>>(list, q, to_prev, to_next, flag_at_prev, flag_at_next, v->put_done + index, epoch);
+    if (engine == ABSINTHE_PUT_KERNEL) {
+        const int lines = list.count * (int)q.planes() * q.HY;
+        put_kernel<<<std::min(lines, sm_count()), kExchangeThreads, 0, s>>>(list, q, to_prev, to_next, flag_at_prev,
+                                                                            flag_at_next, v->put_done + index, epoch);
+        RT(cudaGetLastError());
+        return 0;
+    }
+    if ((rc = copy_rows(v, *g, to_prev, q.HY, true, s))) return rc;
+    if ((rc = copy_rows(v, *g, to_next, q.Y, true, s))) return rc;
+    if (g_drv.StreamWriteValue64) {                       // ordered after the copies, with a memory barrier
+        CUresult r1 = g_drv.StreamWriteValue64((CUstream)s, (CUdeviceptr)flag_at_prev, epoch, CU_STREAM_WRITE_VALUE_DEFAULT);
+        CUresult r2 = g_drv.StreamWriteValue64((CUstream)s, (CUdeviceptr)flag_at_next, epoch, CU_STREAM_WRITE_VALUE_DEFAULT);
+        if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) return 0;
+        g_drv.StreamWriteValue64 = nullptr;               // not on this memory / driver: raise the flags from a kernel
+    }
+    signal_kernel<<<1, 1, 0, s>>>(flag_at_prev, flag_at_next, epoch);
     RT(cudaGetLastError());
     return 0;
 }
@@ -1333,7 +1384,7 @@ int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
     if (c->waited == c->put) return 0;                    // nothing outstanding
     OnDevice on(v->device);
     if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
-    cudaStream_t s = (cudaStream_t)stream;
+    cudaStream_t u = v->unpack_stream;
     FieldList list{};
     list.count = (int)g->halo_fields.size();
     for (int n = 0; n < list.count; ++n) list.ptr[n] = v->fields[g->halo_fields[n]].ptr;
@@ -1341,14 +1392,33 @@ int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
     const unsigned long long epoch = c->put;
     const size_t slot = (c->face_doubles + 15) / 16 * 16;
     const size_t parity = (size_t)(epoch & 1);
-    const double* from_prev = v->window + c->data + (2 * parity + 0) * slot;
-    const double* from_next = v->window + c->data + (2 * parity + 1) * slot;
-    long total = 2L * list.count * q.planes() * q.HY * q.row();
-    int blocks = std::min(launch_grid(total, 256), sm_count() * 2);
-    wait_kernel<<<blocks, 256, 0, s>>>(list, q, from_prev, from_next,
-                                       (const unsigned long long*)(v->window + c->flags), epoch);
-    RT(cudaGetLastError());
-    RT(cudaEventRecord(c->unpacked, s));
+    double* from_prev = v->window + c->data + (2 * parity + 0) * slot;
+    double* from_next = v->window + c->data + (2 * parity + 1) * slot;
+    unsigned long long* flags = (unsigned long long*)(v->window + c->flags);
+    // the halos must not be overwritten before the kernels already enqueued on the caller's stream have read them
+    RT(cudaEventRecord(c->unpacked, (cudaStream_t)stream));
+    RT(cudaStreamWaitEvent(u, c->unpacked, 0));
+    bool waited = false;
+    if (g_drv.StreamWaitValue64) {
+        CUresult r1 = g_drv.StreamWaitValue64((CUstream)u, (CUdeviceptr)flags, epoch, CU_STREAM_WAIT_VALUE_GEQ);
+        CUresult r2 = g_drv.StreamWaitValue64((CUstream)u, (CUdeviceptr)(flags + 1), epoch, CU_STREAM_WAIT_VALUE_GEQ);
+        waited = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
+        if (!waited) g_drv.StreamWaitValue64 = nullptr;
+    }
+    if (!waited) {
+        await_kernel<<<1, 1, 0, u>>>(flags, epoch);
+        RT(cudaGetLastError());
+    }
+    if (c->engine == ABSINTHE_PUT_KERNEL) {
+        const int lines = list.count * (int)q.planes() * q.HY;
+        unpack_kernel<<<std::min(lines, sm_count()), kExchangeThreads, 0, u>>>(list, q, from_prev, from_next);
+        RT(cudaGetLastError());
+    } else {
+        if ((rc = copy_rows(v, *g, from_prev, 0, false, u))) return rc;
+        if ((rc = copy_rows(v, *g, from_next, q.Y + q.HY, false, u))) return rc;
+    }
+    RT(cudaEventRecord(c->unpacked, u));
+    RT(cudaStreamWaitEvent((cudaStream_t)stream, c->unpacked, 0));
     c->waited = epoch;
     return 0;
 }

@@ -160,19 +160,27 @@ class P2PExchange:
         if world > 1:
             dist.barrier(group=process_group)          # nobody PUTs into a window that is not mapped yet
         self.comm = None
+        # default engine of update_async per group: the successor of a group reads its halos at once
+        self.engines = {g: ("kernel" if g < variant.n_groups else "copy") for g in range(1, variant.n_groups + 1)}
 
-    def update_async(self, group):
+    def update_async(self, group, engine=None):
+        """PUT on a side stream.  ``engine``: "kernel" when the very next kernel reads these halos (lowest latency),
+        "copy" when the exchange overlaps a compute kernel that does not (the copy engines take no SM resources
+        from it).  Default: "kernel" for the last group of the variant and for every group but the last of a
+        multi-group variant (its successor reads the halos), "copy" otherwise."""
         import torch
         if self.comm is None:
             self.comm = torch.cuda.Stream(device=self.v.device)
+        if engine is None:
+            engine = self.engines.get(group, "kernel")
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(self.v.device))
         self.comm.wait_event(ready)
-        self.v.put_group(group, stream=self.comm)
+        self.v.put_group(group, stream=self.comm, engine=engine)
 
     def wait(self, group):
         self.v.wait_group(group)
 
-    def update(self, group):
-        self.v.put_group(group)
+    def update(self, group, engine="kernel"):
+        self.v.put_group(group, engine=engine)
         self.v.wait_group(group)

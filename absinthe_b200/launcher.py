@@ -93,7 +93,7 @@ def load_library(path=None):
     lib.absinthe_variant_unpack_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p, c.c_void_p, c.c_void_p]
     lib.absinthe_comm_create.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_char_p]
     lib.absinthe_comm_connect.argtypes = [c.c_void_p, c.c_char_p, c.c_char_p]
-    lib.absinthe_variant_put_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p]
+    lib.absinthe_variant_put_group.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     lib.absinthe_variant_wait_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p]
     lib.absinthe_comm_destroy.argtypes = [c.c_void_p]
     if path == LIB_PATH:
@@ -223,8 +223,11 @@ class Variant:
     def comm_connect(self, prev_handle, next_handle):
         check(self.lib, self.lib.absinthe_comm_connect(self.handle, prev_handle, next_handle), "absinthe_comm_connect")
 
-    def put_group(self, group, stream=None):
-        check(self.lib, self.lib.absinthe_variant_put_group(self.handle, group, _stream_handle(stream, self.device)),
+    def put_group(self, group, stream=None, engine="kernel"):
+        """PUT of the group's edge rows: ``engine`` "kernel" (one small kernel, lowest latency) or "copy" (copy
+        engines, takes nothing from a compute kernel running at the same time)."""
+        check(self.lib, self.lib.absinthe_variant_put_group(self.handle, group, {"kernel": 0, "copy": 1}[engine],
+                                                            _stream_handle(stream, self.device)),
               "absinthe_variant_put_group")
 
     def wait_group(self, group, stream=None):

@@ -170,23 +170,29 @@ int absinthe_make_periodic_ik(double* d_field, int X, int Y, int Z, int HX, int 
  * and exports it as a 64-byte CUDA IPC handle; the host side passes the handles of ranks r-1 and r+1
  * (mod n) to absinthe_comm_connect by whatever channel it has (torch.distributed, MPI, a file).
  *
- *   PUT  (absinthe_variant_put_group):  one kernel stores the first / last HY interior rows of all outputs
- *        of the group -- every plane, full padded width, so i/k halos travel along -- straight into the
- *        neighbours' windows through peer-mapped pointers and then raises their arrival flags.
- *   WAIT (absinthe_variant_wait_group): one kernel waits for both neighbours' flags of the matching PUT
- *        and copies the received rows into the low / high j-halo.
+ *   PUT  (absinthe_variant_put_group):  the first / last HY interior rows of all outputs of the group -- every
+ *        plane, full padded width, so i/k halos travel along -- go straight into the neighbours' windows through
+ *        peer-mapped pointers, then their arrival flags are raised.  `engine` picks who moves the rows:
+ *        ABSINTHE_PUT_KERNEL  one small kernel (lowest latency: for halos the very next kernel reads);
+ *        ABSINTHE_PUT_COPY    the copy engines (strided 2-D copies + a stream memory operation for the flag):
+ *                             no SM, no register, no shared memory is taken from a compute kernel that runs at
+ *                             the same time -- for exchanges that overlap the next group's kernel.
+ *   WAIT (absinthe_variant_wait_group): on a stream of the library, wait for both neighbours' flags of the
+ *        matching PUT and copy the received rows into the low / high j-halo (same engine as the PUT); `stream`
+ *        then waits for that.
  *
- * No pack buffers, no collective library, two launches per group.  Enqueue the PUT after the group's
- * kernel (any stream ordered after it) and the WAIT on the stream of the kernel that reads the halos --
- * at the latest before the group's kernel runs again: a second PUT of a group without the WAIT of the
- * first fails with -6.  With n = 1 both neighbours are the rank itself and PUT + WAIT equal the periodic
- * update of the j faces. */
+ * No pack buffers, no collective library.  Enqueue the PUT after the group's kernel (any stream ordered after
+ * it) and the WAIT on the stream of the kernel that reads the halos -- at the latest before the group's kernel
+ * runs again: a second PUT of a group without the WAIT of the first fails with -6.  With n = 1 both neighbours
+ * are the rank itself and PUT + WAIT equal the periodic update of the j faces. */
+#define ABSINTHE_PUT_KERNEL 0
+#define ABSINTHE_PUT_COPY 1
 #define ABSINTHE_COMM_HANDLE_BYTES 64
 int absinthe_comm_create(absinthe_variant* v, int rank, int nranks,
                          unsigned char handle[ABSINTHE_COMM_HANDLE_BYTES]);
 int absinthe_comm_connect(absinthe_variant* v, const unsigned char* prev_handle,
                           const unsigned char* next_handle);
-int absinthe_variant_put_group(absinthe_variant* v, int group, void* stream);
+int absinthe_variant_put_group(absinthe_variant* v, int group, int engine, void* stream);
 int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream);
 int absinthe_comm_destroy(absinthe_variant* v);
 

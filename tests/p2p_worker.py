@@ -23,7 +23,7 @@ def program_for(kernel, slab):
     return program
 
 
-def worker(rank, world, port, kernel, slab, steps, result):
+def worker(rank, world, port, kernel, slab, steps, result, engine=None):
     import torch
     import torch.distributed as dist
     from absinthe_b200 import programs as P
@@ -49,7 +49,7 @@ def worker(rank, world, port, kernel, slab, steps, result):
                 if g > 1:
                     exchange.wait(g - 1)
                 v.apply_group(g, with_halo=False)
-                exchange.update_async(g)
+                exchange.update_async(g, engine)
         for g in range(1, v.n_groups + 1):
             exchange.wait(g)
         torch.cuda.synchronize()

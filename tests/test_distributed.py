@@ -148,11 +148,12 @@ def _global_oracle(kernel, slab, world):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("engine", ["kernel", "copy"])
 @pytest.mark.parametrize("kernel", ["diffusion", "fastwaves"])
-def test_p2p_exchange_on_one_rank_is_the_periodic_update(launcher_lib, kernel, tmp_path):
+def test_p2p_exchange_on_one_rank_is_the_periodic_update(launcher_lib, kernel, engine, tmp_path):
     from p2p_worker import worker
     slab = (48, 20, 10)
-    worker(0, 1, 29621, kernel, slab, 2, str(tmp_path / "r%d.npz"))
+    worker(0, 1, 29621, kernel, slab, 2, str(tmp_path / "r%d.npz"), engine)
     want = _global_oracle(kernel, slab, 1)
     got = np.load(str(tmp_path / "r0.npz"))
     for name, w in want.items():
@@ -160,14 +161,16 @@ def test_p2p_exchange_on_one_rank_is_the_periodic_update(launcher_lib, kernel, t
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kernel,world", [("diffusion", 2), ("fastwaves", 2), ("fastwaves", 3)])
-def test_p2p_exchange_between_processes(launcher_lib, kernel, world, tmp_path):
+@pytest.mark.parametrize("kernel,world,engine", [("diffusion", 2, None), ("fastwaves", 2, None), ("fastwaves", 3, None),
+                                                 ("fastwaves", 2, "kernel"), ("diffusion", 3, "copy")])
+def test_p2p_exchange_between_processes(launcher_lib, kernel, world, engine, tmp_path):
     """Ranks are separate processes (CUDA IPC windows); they may share one GPU, so this runs on a 1-GPU box too."""
     from p2p_worker import worker
     slab = (48, 20, 10)
     result = str(tmp_path / "r%d.npz")
     ctx = mp.get_context("spawn")
-    procs = [ctx.Process(target=worker, args=(r, world, 29622 + world, kernel, slab, 3, result)) for r in range(world)]
+    procs = [ctx.Process(target=worker, args=(r, world, 29622 + world, kernel, slab, 3, result, engine))
+             for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
