@@ -109,6 +109,16 @@ class ColumnPlan:
         self.fuse_halo = bool(opts["FUSE_HALO"]) and all(s >= 2 * h for s, h in zip(dims, self.H))
         self.acc = {n: A.stencil_accesses(self.by_name[n]["LAMBDA"]) for n in self.names}
         self._schedule()
+        if col.get("MERGE"):
+            # The tile counts of the variant description are a cache-blocking choice of the model; results do not
+            # depend on them.  A column kernel blocks for shared memory per plane, not per tile: with MERGE it
+            # walks whole columns of its own shape -- the k-tiles of a column are merged (no pipeline refill per
+            # k-tile) and x/y extents follow the warp grid instead of tiles narrower than a strip.
+            self.N = (A.ceil_div(dims[0], self.wx * self.useful), A.ceil_div(dims[1], self.wy * self.rj), 1)
+            geo = [tile_geometry(s, n) for s, n in zip(dims, self.N)]
+            self.T = tuple(g[0] for g in geo)
+            self.O = tuple(g[1] for g in geo)
+            self.tiles = self.N[0] * self.N[1] * self.N[2]
         self._geometry(col.get("SLOTS"))
         self._arguments()
 
@@ -295,6 +305,9 @@ class ColumnPlan:
             off += 8
         self.args.append(("tilectl", off, None, None))
         off += 8
+        if self.fuse_halo:
+            self.args.append(("remote", off, None, None))
+            off += 16
         self.scratch_bytes = 0
         if self.wave_sync and self.nsub == (1, 1, 1):
             self.args.append(("scratch", off, None, None))       # wave counters: SYNC_LINES 128-byte lines per CTA
@@ -331,7 +344,8 @@ class ColumnPlan:
                 store = ("__stcs(&o_%s[%d * ROW], %s);" if self.opts["STORE_CS"] else "o_%s[%d * ROW] = %s;") % (s, bb, var)
                 if self.fuse_halo:
                     store += (" if (w.edge || p_%s < HZ || p_%s >= Z - HZ) store_wrapped(o_%s, %d * (long)ROW, "
-                              "w.oi + col, w.oj + row0 + %d, p_%s, %s);" % (s, s, s, bb, bb, s, var))
+                              "w.oi + col, w.oj + row0 + %d, p_%s, %s, %d, prm.remote[0], prm.remote[1]);"
+                              % (s, s, s, bb, bb, s, var, self.outputs.index(s)))
                 lines.append("if (ok_%d && pk_%s) { %s }" % (bb, s, store))
         for dst, src in self.carries:
             lines.append("%s = %s;" % (dst, src))

@@ -385,7 +385,7 @@ struct Field {
 };
 
 struct Arg {
-    enum Type { kMap, kPtr, kTileCtl, kScratch } type;
+    enum Type { kMap, kPtr, kTileCtl, kScratch, kRemote } type;
     size_t offset;
     int field = -1;
     unsigned box[3] = {0, 0, 0};
@@ -571,6 +571,8 @@ int parse_descriptor(absinthe_variant* v, const char* text) {
                 a.type = Arg::kTileCtl;
             } else if (type == "scratch") {
                 a.type = Arg::kScratch;
+            } else if (type == "remote") {
+                a.type = Arg::kRemote;
             } else {
                 return fail(-2, "descriptor: unknown arg type '%s'", type.c_str());
             }
@@ -644,6 +646,17 @@ int build_params(absinthe_variant* v, Group& g) {
         }
     }
     return 0;
+}
+
+// neighbours' exchange windows for the j-wrapped copies of a fused-halo kernel (null: the rank's own j-halo)
+bool set_remote(Group& g, double* to_prev, double* to_next) {
+    for (const Arg& a : g.args)
+        if (a.type == Arg::kRemote) {
+            double* both[2] = {to_prev, to_next};
+            std::memcpy(g.params.data() + a.offset, both, sizeof(both));
+            return true;
+        }
+    return false;
 }
 
 void set_tilectl(Group& g, int step, int count) {
@@ -1375,6 +1388,46 @@ int absinthe_variant_put_group(absinthe_variant* v, int group, int engine, void*
     return 0;
 }
 
+int absinthe_variant_apply_group_put(absinthe_variant* v, int group, void* stream) {
+    absinthe_variant::CommGroup* c = nullptr;
+    Group* g = nullptr;
+    size_t index = 0;
+    int rc = comm_group(v, group, &c, &g, &index);
+    if (rc) return rc;
+    if (!c || !g->fused_halo) {                           // nothing to push from inside the kernel: kernel, then PUT
+        if ((rc = absinthe_variant_apply_group(v, group, 0, stream))) return rc;
+        return c ? absinthe_variant_put_group(v, group, ABSINTHE_PUT_KERNEL, stream) : 0;
+    }
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
+    if (c->put != c->waited)
+        return fail(-6, "group %d: the previous PUT has not been waited for (absinthe_variant_wait_group)", group);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (c->waited >= 1) RT(cudaStreamWaitEvent(s, c->unpacked, 0));
+    const unsigned long long epoch = c->put + 1;
+    const size_t slot = (c->face_doubles + 15) / 16 * 16;
+    const size_t parity = (size_t)(epoch & 1);
+    double* to_prev = v->window_prev + c->data + (2 * parity + 1) * slot;
+    double* to_next = v->window_next + c->data + (2 * parity + 0) * slot;
+    if (!set_remote(*g, to_prev, to_next)) return fail(-3, "kernel of group %d has no slot for the exchange windows", group);
+    rc = launch_group(v, *g, false, s);
+    set_remote(*g, nullptr, nullptr);                     // plain applications keep writing the rank's own halo
+    if (rc) return rc;
+    c->put = epoch;
+    c->engine = ABSINTHE_PUT_KERNEL;
+    unsigned long long* flag_at_prev = (unsigned long long*)(v->window_prev + c->flags) + 1;
+    unsigned long long* flag_at_next = (unsigned long long*)(v->window_next + c->flags) + 0;
+    if (g_drv.StreamWriteValue64) {                       // after the kernel, with a memory barrier
+        CUresult r1 = g_drv.StreamWriteValue64((CUstream)s, (CUdeviceptr)flag_at_prev, epoch, CU_STREAM_WRITE_VALUE_DEFAULT);
+        CUresult r2 = g_drv.StreamWriteValue64((CUstream)s, (CUdeviceptr)flag_at_next, epoch, CU_STREAM_WRITE_VALUE_DEFAULT);
+        if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) return 0;
+        g_drv.StreamWriteValue64 = nullptr;
+    }
+    signal_kernel<<<1, 1, 0, s>>>(flag_at_prev, flag_at_next, epoch);
+    RT(cudaGetLastError());
+    return 0;
+}
+
 int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
     absinthe_variant::CommGroup* c = nullptr;
     Group* g = nullptr;
@@ -1384,7 +1437,10 @@ int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
     if (c->waited == c->put) return 0;                    // nothing outstanding
     OnDevice on(v->device);
     if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
-    cudaStream_t u = v->unpack_stream;
+    // the kernel engine serves halos the very next kernel reads: wait and unpack on the caller's own stream (no
+    // event hops); the copy engine works beside the compute kernels of the caller's stream, on a stream of its own
+    const bool inline_wait = c->engine == ABSINTHE_PUT_KERNEL;
+    cudaStream_t u = inline_wait ? (cudaStream_t)stream : v->unpack_stream;
     FieldList list{};
     list.count = (int)g->halo_fields.size();
     for (int n = 0; n < list.count; ++n) list.ptr[n] = v->fields[g->halo_fields[n]].ptr;
@@ -1396,8 +1452,10 @@ int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
     double* from_next = v->window + c->data + (2 * parity + 1) * slot;
     unsigned long long* flags = (unsigned long long*)(v->window + c->flags);
     // the halos must not be overwritten before the kernels already enqueued on the caller's stream have read them
-    RT(cudaEventRecord(c->unpacked, (cudaStream_t)stream));
-    RT(cudaStreamWaitEvent(u, c->unpacked, 0));
+    if (!inline_wait) {
+        RT(cudaEventRecord(c->unpacked, (cudaStream_t)stream));
+        RT(cudaStreamWaitEvent(u, c->unpacked, 0));
+    }
     bool waited = false;
     if (g_drv.StreamWaitValue64) {
         CUresult r1 = g_drv.StreamWaitValue64((CUstream)u, (CUdeviceptr)flags, epoch, CU_STREAM_WAIT_VALUE_GEQ);
@@ -1418,7 +1476,7 @@ int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
         if ((rc = copy_rows(v, *g, from_next, q.Y + q.HY, false, u))) return rc;
     }
     RT(cudaEventRecord(c->unpacked, u));
-    RT(cudaStreamWaitEvent((cudaStream_t)stream, c->unpacked, 0));
+    if (!inline_wait) RT(cudaStreamWaitEvent((cudaStream_t)stream, c->unpacked, 0));
     c->waited = epoch;
     return 0;
 }

@@ -112,6 +112,11 @@ class SlabExchange:
         if done is not None:
             torch.cuda.current_stream().wait_event(done)
 
+    def apply(self, group, engine=None):
+        """COMP + PUT of ``group`` (same call as ``P2PExchange.apply``)."""
+        self.v.apply_group(group, with_halo=False)
+        self.update_async(group)
+
     # -- protocol ---------------------------------------------------------------------------
     def update(self, group):
         """PUT + WAIT of every output of ``group`` (the slot after its COMP in the schedule)."""
@@ -177,6 +182,16 @@ class P2PExchange:
         ready.record(torch.cuda.current_stream(self.v.device))
         self.comm.wait_event(ready)
         self.v.put_group(group, stream=self.comm, engine=engine)
+
+    def apply(self, group, engine=None):
+        """COMP + PUT of ``group``: with engine "fused" (the default where the successor reads the halos at once)
+        the kernel itself pushes its edge rows into the neighbours' windows; otherwise kernel, then PUT."""
+        engine = engine or {"kernel": "fused"}.get(self.engines.get(group, "kernel"), "copy")
+        if engine == "fused":
+            self.v.apply_group_put(group)
+        else:
+            self.v.apply_group(group, with_halo=False)
+            self.update_async(group, engine)
 
     def wait(self, group):
         self.v.wait_group(group)

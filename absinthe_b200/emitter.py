@@ -61,7 +61,9 @@ DEFAULTS = {
                                  # memory; "regs": column kernel (column.py) -- a thread owns a column, values
                                  # wanted again at lower planes are carried in registers, no CTA barriers;
                                  # "auto": column kernel for groups whose stencils read each other across k
-    "COLUMN": None,              # column kernel shape: {"WARPS": (WX, WY), "PLANES": planes per TMA box, "SLOTS": ring}
+    "COLUMN": None,              # column kernel shape: {"WARPS": (WX, WY), "PLANES": planes per TMA box, "SLOTS": ring,
+                                 # "UNROLL": ring slots per loop trip, "MERGE": walk whole columns of the kernel's own
+                                 # shape instead of the variant's tiles, "WAVE_SYNC": see column.py}
     "PREFETCH": 2,               # STREAM_K: input planes in flight beyond the ones being read
 }
 FRONT_SLACK = 16                 # doubles before the first box (halo lanes of a warp read below it)
@@ -428,6 +430,9 @@ class GroupPlan:
             off += 8
         self.args.append(("tilectl", off, None, None))
         off += 8
+        if self.fuse_halo:
+            self.args.append(("remote", off, None, None))    # neighbours' exchange windows (multi-GPU fused PUT)
+            off += 16
         self.params_bytes = _round_up(off, 64)
 
     # -- phases -----------------------------------------------------------------------------
@@ -712,6 +717,8 @@ class Plan:
                     lines.append("arg ptr %d %s" % (off, name))
                 elif kind == "scratch":
                     lines.append("arg scratch %d" % off)
+                elif kind == "remote":
+                    lines.append("arg remote %d" % off)
                 else:
                     lines.append("arg tilectl %d" % off)
             for name in g.outputs:

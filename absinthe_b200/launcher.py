@@ -30,6 +30,7 @@ SYMBOLS = [
     "absinthe_variant_apply_host_async", "absinthe_variant_wait_host", "absinthe_compare_fields",
     "absinthe_variant_host_interior",
     "absinthe_comm_create", "absinthe_comm_connect", "absinthe_variant_put_group", "absinthe_variant_wait_group",
+    "absinthe_variant_apply_group_put",
     "absinthe_comm_destroy",
 ]
 COMM_HANDLE_BYTES = 64
@@ -96,6 +97,7 @@ def load_library(path=None):
     lib.absinthe_variant_put_group.argtypes = [c.c_void_p, c.c_int, c.c_int, c.c_void_p]
     lib.absinthe_variant_wait_group.argtypes = [c.c_void_p, c.c_int, c.c_void_p]
     lib.absinthe_comm_destroy.argtypes = [c.c_void_p]
+    lib.absinthe_variant_apply_group_put.argtypes = [c.c_void_p, c.c_int, c.c_void_p]
     if path == LIB_PATH:
         _lib = lib
     return lib
@@ -229,6 +231,11 @@ class Variant:
         check(self.lib, self.lib.absinthe_variant_put_group(self.handle, group, {"kernel": 0, "copy": 1}[engine],
                                                             _stream_handle(stream, self.device)),
               "absinthe_variant_put_group")
+
+    def apply_group_put(self, group, stream=None):
+        """The group's kernel with its j-wrapped copies stored straight into the neighbours' windows, then the flags."""
+        check(self.lib, self.lib.absinthe_variant_apply_group_put(self.handle, group, _stream_handle(stream, self.device)),
+              "absinthe_variant_apply_group_put")
 
     def wait_group(self, group, stream=None):
         check(self.lib, self.lib.absinthe_variant_wait_group(self.handle, group, _stream_handle(stream, self.device)),

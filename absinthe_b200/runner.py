@@ -123,9 +123,8 @@ def run_variant_ranks(stem, runs, rank, world, flush=True, device=0, out=sys.std
             if g > 1:
                 exchange.wait(g - 1)                 # WAIT: this group reads the halos of the previous one
             marks[2 * g - 1].record()
-            variant.apply_group(g, with_halo=False)
+            exchange.apply(g)                        # COMP + PUT (fused into the kernel, or overlapped with the next one)
             marks[2 * g].record()
-            exchange.update_async(g)                 # PUT, overlapped with the next kernel
         for g in groups:
             exchange.wait(g)
         marks[-1].record()

@@ -347,13 +347,13 @@ def run_gpu_arm(args):
                 if record is not None:
                     a, b, c = (torch.cuda.Event(enable_timing=True) for _ in range(3))
                     a.record()
-                    v.apply_group(g, with_halo=False)
-                    b.record()
-                else:
-                    v.apply_group(g, with_halo=False)
                 if exchange is not None:
-                    exchange.update_async(g)      # PUT, overlapped with the next kernels
+                    exchange.apply(g)             # COMP + PUT (overlapped with the next kernels, or fused into this one)
                 else:
+                    v.apply_group(g, with_halo=False)
+                if record is not None:
+                    b.record()
+                if exchange is None:
                     v.halo_group(g)
                 if record is not None:
                     c.record()
@@ -435,6 +435,11 @@ def run_gpu_arm(args):
     for name, g, a, b, c in records:
         kernel_ms.setdefault((name, g), []).append(a.elapsed_time(b))
         halo_ms.setdefault((name, g), []).append(b.elapsed_time(c))
+    # time between the end of the previous group kernel and the start of this one (host enqueue gaps, and on
+    # several GPUs the part of the halo exchange the kernels could not hide)
+    gap_ms = {}
+    for prev, this in zip(records, records[1:]):
+        gap_ms.setdefault((this[0], this[1]), []).append(prev[3].elapsed_time(this[2]))
     breakdown = {}
     dominant = None
     for item in variants:
@@ -444,7 +449,8 @@ def run_gpu_arm(args):
             gbs = item["group_bytes"][g - 1] * points / (k * 1e-3) / 1e9
             label = item["group_names"][g - 1]
             breakdown[label] = {"kernel_ms": round(k, 4), "halo_ms": round(h, 4), "GBps": round(gbs, 1),
-                                "bytes_per_point": item["group_bytes"][g - 1]}
+                                "bytes_per_point": item["group_bytes"][g - 1],
+                                "gap_before_ms": round(statistics.mean(gap_ms.get((item["name"], g), [0.0])), 4)}
             if dominant is None or k > dominant[1]:
                 dominant = (label, k, gbs)
     peaks = {}

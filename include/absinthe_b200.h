@@ -194,6 +194,12 @@ int absinthe_comm_connect(absinthe_variant* v, const unsigned char* prev_handle,
                           const unsigned char* next_handle);
 int absinthe_variant_put_group(absinthe_variant* v, int group, int engine, void* stream);
 int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream);
+/* COMP + PUT in one: the group's kernel itself stores the copies of its edge rows that wrap in j (rows, i/k halos
+ * and corners: what its fused periodic update would write into the rank's own j-halo) into the neighbours'
+ * windows while it computes; after the kernel only the arrival flags are raised.  The exchange then costs the
+ * neighbour's unpack and nothing else on the critical path.  Needs a kernel generated with fused periodic
+ * copies (CUDA.FUSE_HALO); any other group falls back to kernel + ABSINTHE_PUT_KERNEL.  WAIT as above. */
+int absinthe_variant_apply_group_put(absinthe_variant* v, int group, void* stream);
 int absinthe_comm_destroy(absinthe_variant* v);
 
 #ifdef __cplusplus

@@ -42,10 +42,10 @@ def run_check(programs, world=1, rank=0, device=0, windows=None, exchange_kind="
         for g in range(1, v.n_groups + 1):                  # one step, as bench.py runs it
             if exchange is not None and g > 1:
                 exchange.wait(g - 1)
-            v.apply_group(g, with_halo=False)
             if exchange is not None:
-                exchange.update_async(g)
+                exchange.apply(g)
             else:
+                v.apply_group(g, with_halo=False)
                 v.halo_group(g)
         if exchange is not None:
             for g in range(1, v.n_groups + 1):

@@ -95,3 +95,12 @@ def test_auto_picks_column_kernels_for_k_dependent_groups_only():
     q = P.make_program("diffusion", [d], [(2, 4, 3)])
     q["CUDA"] = {"STREAM_K": "auto"}
     assert [g.column for g in Plan(q).groups] == [False]
+
+
+def test_merge_walks_columns_of_the_kernels_own_shape():
+    q = P.make_program("fastwaves", [F], [(9, 16, 6)], domain=(128, 64, 60))
+    q["CUDA"] = {"STREAM_K": "regs", "BLOCK": (2, 1), "COLUMN": {"WARPS": (2, 3), "MERGE": True}}
+    g = Plan(q).groups[0]
+    assert g.N == (3, 11, 1) and g.T == (43, 6, 60) and g.nsub == (1, 1, 1)     # 2 strips of 30 columns, 3 x 2 rows
+    assert g.simulate() == len(g.outputs) * g.rj * g.useful * (4 - g.kmin)
+    assert "tiles 33 " in Plan(P.clone(q)).descriptor_text()

@@ -148,7 +148,7 @@ def _global_oracle(kernel, slab, world):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("engine", ["kernel", "copy"])
+@pytest.mark.parametrize("engine", ["kernel", "copy", "fused"])
 @pytest.mark.parametrize("kernel", ["diffusion", "fastwaves"])
 def test_p2p_exchange_on_one_rank_is_the_periodic_update(launcher_lib, kernel, engine, tmp_path):
     from p2p_worker import worker
@@ -162,7 +162,7 @@ def test_p2p_exchange_on_one_rank_is_the_periodic_update(launcher_lib, kernel, e
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("kernel,world,engine", [("diffusion", 2, None), ("fastwaves", 2, None), ("fastwaves", 3, None),
-                                                 ("fastwaves", 2, "kernel"), ("diffusion", 3, "copy")])
+                                                 ("fastwaves", 2, "kernel"), ("diffusion", 3, "copy"), ("fastwaves", 3, "fused")])
 def test_p2p_exchange_between_processes(launcher_lib, kernel, world, engine, tmp_path):
     """Ranks are separate processes (CUDA IPC windows); they may share one GPU, so this runs on a 1-GPU box too."""
     from p2p_worker import worker

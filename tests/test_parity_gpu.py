@@ -43,6 +43,8 @@ OPTIONS = [
     ("poll-warp-generic", {"POLL_WARP": True, "THREADS": 128}),
     ("column", {"STREAM_K": "regs"}),
     ("column-auto", {"STREAM_K": "auto", "INLINE": "all", "BLOCK": (2, 1), "SHUFFLE": True, "FUSE_HALO": True}),
+    ("column-merge", {"STREAM_K": "auto", "INLINE": "all", "BLOCK": (1, 1), "FUSE_HALO": True, "THREADS": 128,
+                      "COLUMN": {"MERGE": True, "WARPS": (1, 3), "UNROLL": 1}}),
     ("column-rj2-planes2-halo", {"STREAM_K": "regs", "BLOCK": (2, 1), "COLUMN": {"WARPS": (1, 2), "PLANES": 2},
                                  "FUSE_HALO": True}),
     ("column-rj3-planes3", {"STREAM_K": "regs", "BLOCK": (3, 1),

@@ -49,6 +49,33 @@ def plan(args):
                    "variants": variants}, handle, indent=1)
 
 
+def _compile(job):
+    from absinthe_b200.generator import build_variant
+    try:
+        build_variant(job)
+        return None
+    except Exception as exc:
+        return str(exc)[-300:]
+
+
+def build(args):
+    """Compile every variant of a study (no GPU needed): the cache travels to the GPU box with the snapshot."""
+    from concurrent.futures import ProcessPoolExecutor
+    from absinthe_b200 import programs as P
+    study = json.load(open(args.variants))
+    kernel, domain = study["kernel"], tuple(study["domain"])
+    seq = P.KERNELS[kernel][1]()
+    jobs = []
+    for item in study["variants"]:
+        program = P.make_program(kernel, P.split_sequence(seq, item["assignment"]), [tuple(t) for t in item["tiles"]],
+                                 domain=domain)
+        program["CUDA"] = json.loads(args.cuda) if args.cuda else {}
+        jobs.append(program)
+    with ProcessPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
+        errors = [e for e in pool.map(_compile, jobs) if e]
+    print(len(jobs), "variants,", len(errors), "failures", errors[:3])
+
+
 def measure(args):
     import torch
     from absinthe_b200 import programs as P
@@ -105,8 +132,11 @@ def main():
     b.add_argument("--runs", type=int, default=4)
     b.add_argument("--cuda", default="")
     b.add_argument("--out", default="")
+    c = sub.add_parser("build")
+    c.add_argument("--variants", required=True)
+    c.add_argument("--cuda", default="")
     args = ap.parse_args()
-    plan(args) if args.cmd == "plan" else measure(args)
+    {"plan": plan, "measure": measure, "build": build}[args.cmd](args)
 
 
 if __name__ == "__main__":
