@@ -1336,6 +1336,8 @@ static int copy_rows(absinthe_variant* v, const Group& g, double* buffer, long j
     return 0;
 }
 
+static int unpack_on(absinthe_variant* v, absinthe_variant::CommGroup* c, Group* g, cudaStream_t u);
+
 int absinthe_variant_put_group(absinthe_variant* v, int group, int engine, void* stream) {
     absinthe_variant::CommGroup* c = nullptr;
     Group* g = nullptr;
@@ -1375,17 +1377,25 @@ int absinthe_variant_put_group(absinthe_variant* v, int group, int engine, void*
         RT(cudaGetLastError());
         return 0;
     }
+    // the unpack of this exchange goes to the library's stream right away: behind the group's kernel (everything
+    // `s` holds up to here), it waits for the neighbours' flags and fills the j-halos while the caller's stream
+    // computes the next groups; the WAIT then only waits for its event
+    RT(cudaEventRecord(c->unpacked, s));
+    RT(cudaStreamWaitEvent(v->unpack_stream, c->unpacked, 0));
     if ((rc = copy_rows(v, *g, to_prev, q.HY, true, s))) return rc;
     if ((rc = copy_rows(v, *g, to_next, q.Y, true, s))) return rc;
+    bool raised = false;
     if (g_drv.StreamWriteValue64) {                       // ordered after the copies, with a memory barrier
         CUresult r1 = g_drv.StreamWriteValue64((CUstream)s, (CUdeviceptr)flag_at_prev, epoch, CU_STREAM_WRITE_VALUE_DEFAULT);
         CUresult r2 = g_drv.StreamWriteValue64((CUstream)s, (CUdeviceptr)flag_at_next, epoch, CU_STREAM_WRITE_VALUE_DEFAULT);
-        if (r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS) return 0;
-        g_drv.StreamWriteValue64 = nullptr;               // not on this memory / driver: raise the flags from a kernel
+        raised = r1 == CUDA_SUCCESS && r2 == CUDA_SUCCESS;
+        if (!raised) g_drv.StreamWriteValue64 = nullptr;  // not on this memory / driver: raise the flags from a kernel
     }
-    signal_kernel<<<1, 1, 0, s>>>(flag_at_prev, flag_at_next, epoch);
-    RT(cudaGetLastError());
-    return 0;
+    if (!raised) {
+        signal_kernel<<<1, 1, 0, s>>>(flag_at_prev, flag_at_next, epoch);
+        RT(cudaGetLastError());
+    }
+    return unpack_on(v, c, g, v->unpack_stream);
 }
 
 int absinthe_variant_apply_group_put(absinthe_variant* v, int group, void* stream) {
@@ -1428,19 +1438,8 @@ int absinthe_variant_apply_group_put(absinthe_variant* v, int group, void* strea
     return 0;
 }
 
-int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
-    absinthe_variant::CommGroup* c = nullptr;
-    Group* g = nullptr;
-    size_t index = 0;
-    int rc = comm_group(v, group, &c, &g, &index);
-    if (rc || !c) return rc;
-    if (c->waited == c->put) return 0;                    // nothing outstanding
-    OnDevice on(v->device);
-    if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
-    // the kernel engine serves halos the very next kernel reads: wait and unpack on the caller's own stream (no
-    // event hops); the copy engine works beside the compute kernels of the caller's stream, on a stream of its own
-    const bool inline_wait = c->engine == ABSINTHE_PUT_KERNEL;
-    cudaStream_t u = inline_wait ? (cudaStream_t)stream : v->unpack_stream;
+// wait for both neighbours' flags of the outstanding PUT on stream `u` and fill the j-halos; records `unpacked`
+static int unpack_on(absinthe_variant* v, absinthe_variant::CommGroup* c, Group* g, cudaStream_t u) {
     FieldList list{};
     list.count = (int)g->halo_fields.size();
     for (int n = 0; n < list.count; ++n) list.ptr[n] = v->fields[g->halo_fields[n]].ptr;
@@ -1451,11 +1450,6 @@ int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
     double* from_prev = v->window + c->data + (2 * parity + 0) * slot;
     double* from_next = v->window + c->data + (2 * parity + 1) * slot;
     unsigned long long* flags = (unsigned long long*)(v->window + c->flags);
-    // the halos must not be overwritten before the kernels already enqueued on the caller's stream have read them
-    if (!inline_wait) {
-        RT(cudaEventRecord(c->unpacked, (cudaStream_t)stream));
-        RT(cudaStreamWaitEvent(u, c->unpacked, 0));
-    }
     bool waited = false;
     if (g_drv.StreamWaitValue64) {
         CUresult r1 = g_drv.StreamWaitValue64((CUstream)u, (CUdeviceptr)flags, epoch, CU_STREAM_WAIT_VALUE_GEQ);
@@ -1472,12 +1466,32 @@ int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
         unpack_kernel<<<std::min(lines, sm_count()), kExchangeThreads, 0, u>>>(list, q, from_prev, from_next);
         RT(cudaGetLastError());
     } else {
+        int rc = 0;
         if ((rc = copy_rows(v, *g, from_prev, 0, false, u))) return rc;
         if ((rc = copy_rows(v, *g, from_next, q.Y + q.HY, false, u))) return rc;
     }
     RT(cudaEventRecord(c->unpacked, u));
-    if (!inline_wait) RT(cudaStreamWaitEvent((cudaStream_t)stream, c->unpacked, 0));
-    c->waited = epoch;
+    return 0;
+}
+
+int absinthe_variant_wait_group(absinthe_variant* v, int group, void* stream) {
+    absinthe_variant::CommGroup* c = nullptr;
+    Group* g = nullptr;
+    size_t index = 0;
+    int rc = comm_group(v, group, &c, &g, &index);
+    if (rc || !c) return rc;
+    if (c->waited == c->put) return 0;                    // nothing outstanding
+    OnDevice on(v->device);
+    if (!on.ok) return fail(-3, "cannot switch to device %d", v->device);
+    if (c->engine == ABSINTHE_PUT_KERNEL) {
+        // halos the very next kernel reads: wait and unpack on the caller's own stream, no event hops
+        if ((rc = unpack_on(v, c, g, (cudaStream_t)stream))) return rc;
+    } else {
+        // copy engine: the unpack was enqueued with the PUT (on the library's stream, behind the group's kernel)
+        // and has usually long finished; the caller's stream only waits for its event
+        RT(cudaStreamWaitEvent((cudaStream_t)stream, c->unpacked, 0));
+    }
+    c->waited = c->put;
     return 0;
 }
 

@@ -23,10 +23,16 @@ B200_SMEM_PER_CTA = 227 * 1024
 CPU_MEMORY = {"RW BODY": -2.23e-7, "ST BODY": 5.71e-7, "RW PEEL": -1.25e-6, "ST PEEL": 5.25e-6}
 CPU_CACHE = {"BODY": 9.44e-8, "PEEL": 9.95e-7}
 
-# GPU fit of the training sweeps (profiles/r01_fit_nonnegative_intercept.json, absinthe_b200/fit.py with
-# a launch-latency intercept of 10.2 us and non-negative coefficients; the RW terms fit to zero)
-B200_MEMORY = {"RW BODY": 0.0, "ST BODY": 4.91e-9, "RW PEEL": 0.0, "ST PEEL": 2.75e-8}
-B200_CACHE = {"BODY": 1.17e-10, "PEEL": 2.33e-10}
+# GPU fit of the training sweeps, round 2 (profiles/r02_fit.json): `fitcache.py -g -s 1` / `fitddr.py -g -s 1` on the
+# B200 -- every tile of a training program runs (20 per SM), so the fit sees throughput, not one launch latency --
+# fitted with absinthe_b200/fit.py (LAD, --tiles-per-core 20 --intercept).  CACHE: R2 0.957 on the 309 fitcache
+# programs with >= 12 fetches.  MEMORY: the IN1..3 BD0 programs (R2 0.94, all coefficients positive without
+# constraint); with boundary depth >= 1 the 27 haloed input streams of a fitddr program no longer fit one
+# shared-memory stage, the kernels fall back to sub-tiles of a few dozen points and leave the linear regime
+# (R2 0.31 over all programs).  Round 1 (one wave of tiles = launch latency) had
+# RW 0 / ST BODY 4.91e-9 / ST PEEL 2.75e-8 and CACHE 1.17e-10 / 2.33e-10.
+B200_MEMORY = {"RW BODY": 7.31e-10, "ST BODY": 1.258e-9, "RW PEEL": 2.2081e-8, "ST PEEL": 5.849e-9}
+B200_CACHE = {"BODY": 7.016e-11, "PEEL": 3.950e-11}
 
 KERNELS = {
     "diffusion": (S.diffusion_stencils, S.diffusion_sequence, S.DIFFUSION_OUTPUTS, S.DIFFUSION_CONSTANTS),
