@@ -161,9 +161,19 @@ class P2PExchange:
         if world > 1:
             handles = [None] * world
             dist.all_gather_object(handles, mine, group=process_group)
-        variant.comm_connect(handles[self.prev], handles[self.next])
+        problem = None
+        try:
+            variant.comm_connect(handles[self.prev], handles[self.next])
+        except Exception as exc:                       # e.g. no peer access between two devices
+            problem = "rank %d: %s" % (rank, exc)
         if world > 1:
-            dist.barrier(group=process_group)          # nobody PUTs into a window that is not mapped yet
+            # every rank learns whether all windows are mapped (this is also the barrier before the first PUT);
+            # a failure anywhere raises everywhere, so that the caller can fall back on all ranks alike
+            problems = [None] * world
+            dist.all_gather_object(problems, problem, group=process_group)
+            problem = next((p for p in problems if p), None)
+        if problem:
+            raise RuntimeError("P2P exchange unavailable (%s)" % problem)
         self.comm = None
         # default engine of update_async per group: the successor of a group reads its halos at once
         self.engines = {g: ("kernel" if g < variant.n_groups else "copy") for g in range(1, variant.n_groups + 1)}

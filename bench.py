@@ -324,7 +324,14 @@ def run_gpu_arm(args):
             ins.append(t)
         outs = [v.empty_field() for _ in v.outputs]
         v.bind(ins, outs)
-        exchange = Exchange(v, world, rank) if world > 1 else None
+        exchange = None
+        if world > 1:
+            try:
+                exchange = Exchange(v, world, rank)
+            except RuntimeError as exc:                # raised on every rank alike (see P2PExchange)
+                if rank == 0:
+                    print("falling back to the NCCL exchange:", exc, file=sys.stderr)
+                exchange, args.exchange = SlabExchange(v, world, rank), "nccl (p2p unavailable)"
         analysed = P.clone(program)
         from absinthe_b200.analysis import analyse
         analyse(analysed)
