@@ -80,6 +80,9 @@ def extra_programs():
         program = P.make_program(kernel, groups, [(2, 16, 5)] * len(groups), variant=kernel + "-64x64x60")
         program["CUDA"] = dict(cuda)
         out.append(("small:" + kernel, program))
+    # BASELINE.json configs[1]: a few programs of the training sweeps, every tile executed (20 per SM)
+    for family, variant in (("fitcache", "PT12"), ("fitcache", "PT20"), ("fitddr", "IN1BD0"), ("fitddr", "IN3BD0")):
+        out.append(("training:%s-%s" % (family, variant), P.training_program(family, variant, (50, 5, 8), stride=1)))
     return out
 
 
@@ -105,11 +108,15 @@ def scale_tiles(program, domain):
     return q
 
 
+def template_of(program):
+    return "template_training.cu" if program.get("TRAINING") else "template_tiling.cu"
+
+
 def prebuild_variants():
     from absinthe_b200.generator import build_variant
     from absinthe_b200 import programs as P
     for _, program in workload_programs() + extra_programs():
-        build_variant(P.clone(program))
+        build_variant(P.clone(program), template_of(program))
 
 
 def prebuild():
@@ -579,7 +586,7 @@ def measure_extras(peak):
     out = {}
     gen = torch.Generator(device="cuda").manual_seed(99)
     for label, program in extra_programs():
-        v = Variant.from_program(P.clone(program))
+        v = Variant.from_program(P.clone(program), template_of(program))
         dims = (v.X, v.Y, v.Z, v.HX, v.HY, v.HZ)
         ins = []
         for _ in v.inputs:
@@ -588,6 +595,17 @@ def measure_extras(peak):
             ins.append(t)
         outs = [v.empty_field() for _ in v.outputs]
         v.bind(ins, outs)
+        if label.startswith("training:"):       # the training protocol of the launcher (ref template_training.cpp:276-311)
+            total, _ = v.run(12, flush=False, training=True)
+            ms = statistics.median(total)
+            tiles = 2 * 2 * 5 * program["TRAINING"]["CORES"]
+            out[label] = {"domain": [v.X, v.Y, v.Z], "tile": [v.X // 2, v.Y // 2, v.Z // (5 * program["TRAINING"]["CORES"])],
+                          "tiles": tiles, "ms": round(ms, 4), "ns_per_tile_and_sm": round(ms * 1e6 / (tiles / 148.0), 1),
+                          "mpoints_s": round(v.points / ms / 1e3, 1)}
+            v.close()
+            del ins, outs
+            torch.cuda.empty_cache()
+            continue
         small = label.startswith("small:")
         reps = 300 if small else 12
         for _ in range(3):

@@ -62,3 +62,27 @@ def test_workload_is_the_named_configuration():
     for outer_full, outer_slab in zip(programs["fastwaves"]["TILING"]["GROUPS"], slab["TILING"]["GROUPS"]):
         a, b = outer_full["GROUPS"][0], outer_slab["GROUPS"][0]
         assert (a["NX"], a["NY"]) == (b["NX"], b["NY"]) and b["NZ"] == 1
+
+
+def test_extras_cover_the_other_baseline_configs():
+    """BASELINE.json configs[0..3] get driver-visible numbers in the `extras` block of the bench line."""
+    labels = [label for label, _ in bench.extra_programs()]
+    assert "advection:auto" in labels and "advection:hand(1,1,Z)" in labels
+    assert {"small:diffusion", "small:advection", "small:fastwaves"} <= set(labels)
+    assert sum(label.startswith("training:") for label in labels) == 4
+    by_label = dict(bench.extra_programs())
+    hand = by_label["advection:hand(1,1,Z)"]["TILING"]["GROUPS"][0]["GROUPS"][0]
+    assert (hand["NX"], hand["NY"], hand["NZ"]) == (1, 1, 80)            # ref advection.py:145-160, one tile per plane
+    assert by_label["small:fastwaves"]["X"] == 64 and by_label["training:fitddr-IN3BD0"]["TRAINING"]["STRIDE"] == 1
+    assert bench.template_of(by_label["training:fitcache-PT12"]) == "template_training.cu"
+
+
+def test_reference_arm_names_its_sample(monkeypatch):
+    """--impl reference states which domain the reference binary ran on (the full one when it is shipped)."""
+    monkeypatch.setattr(bench, "cpu_reference_time", lambda name, steps, warmup, prefix="bench_": (100.0, 3, 16))
+    full = bench.cpu_baseline(steps=3, warmup=1, full=True)
+    assert full["sample_domain"] == [1024, 1024, 80] and "full 1024x1024x80 domain" in full["sample"]
+    slab = bench.cpu_baseline(steps=3, warmup=1)
+    assert slab["sample_domain"] == [1024, 1024, 8] and slab["kind"] == "reference" and slab["cores"] == 16
+    # value: two sequences over the sample's points per summed milliseconds
+    assert abs(full["value"] - 2 * 1024 * 1024 * 80 / 0.2 / 1e6) < 1e-6
