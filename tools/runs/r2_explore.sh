@@ -4,10 +4,10 @@
 mkdir -p gpurun_out
 ROOT=$PWD
 export PYTHONPATH=$ROOT:$PYTHONPATH
-cd $ROOT/build/explore/fastwaves
+K=${K:-fastwaves}; cd $ROOT/build/explore/$K
 ( time bash run.sh > output.txt ) > $ROOT/gpurun_out/r2_explore_run.log 2>&1; echo "run.sh rc $?"
 cd $ROOT/build/explore
-python $ROOT/fastwaves.py -p output.txt -f ./fastwaves > $ROOT/gpurun_out/r2_explore_parse.log 2>&1; echo "parse rc $?"
-python -m absinthe_b200.report ./fastwaves > $ROOT/gpurun_out/r2_explore_report.json 2>&1; echo "report rc $?"
-cp fastwaves/results.csv $ROOT/gpurun_out/r2_explore_results.csv; cp fastwaves/estimates.csv $ROOT/gpurun_out/r2_explore_estimates.csv; cp fastwaves/summary.csv $ROOT/gpurun_out/r2_explore_summary.csv
-tail -30 $ROOT/gpurun_out/r2_explore_report.json
+python $ROOT/$K.py -p output.txt -f ./$K > $ROOT/gpurun_out/r2_explore_parse.log 2>&1; echo "parse rc $?"
+python -m absinthe_b200.report ./$K > $ROOT/gpurun_out/r2_explore_report_$K.json 2>&1; echo "report rc $?"
+mkdir -p $ROOT/gpurun_out/explore_$K; cp $K/results.csv $K/estimates.csv $K/summary.csv $ROOT/gpurun_out/explore_$K/
+tail -6 $ROOT/gpurun_out/r2_explore_report_$K.json
