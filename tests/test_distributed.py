@@ -203,3 +203,42 @@ def test_second_put_without_wait_is_refused(launcher_lib):
     exchange.update(1)
     torch.cuda.synchronize()
     v.close()
+
+
+def test_p2p_exchange_picks_engines_and_agrees_on_failure(monkeypatch):
+    """Host logic of P2PExchange without a GPU: the successor of a group reads its halos at once (fused push), the
+    last group's exchange overlaps whatever comes next (copy engines); a connect failure raises a RuntimeError."""
+    from absinthe_b200.distributed import P2PExchange
+
+    class FakeVariant:
+        n_groups, device = 3, 0
+        calls = []
+
+        def comm_create(self, rank, world):
+            return b"h" * 64
+
+        def comm_connect(self, prev, nxt):
+            self.calls.append(("connect", prev, nxt))
+
+        def apply_group_put(self, group, stream=None):
+            self.calls.append(("fused", group))
+
+        def apply_group(self, group, with_halo=True, stream=None):
+            self.calls.append(("apply", group, with_halo))
+
+    v = FakeVariant()
+    ex = P2PExchange(v, 1, 0)
+    assert ex.engines == {1: "kernel", 2: "kernel", 3: "copy"}
+    ex.apply(1)
+    assert v.calls[-1] == ("fused", 1)
+    ex.update_async = lambda group, engine=None: v.calls.append(("put", group, engine))
+    ex.apply(3)
+    assert v.calls[-2:] == [("apply", 3, False), ("put", 3, "copy")]
+    ex.apply(2, "kernel")
+    assert v.calls[-2:] == [("apply", 2, False), ("put", 2, "kernel")]
+
+    class Broken(FakeVariant):
+        def comm_connect(self, prev, nxt):
+            raise OSError("no peer access")
+    with pytest.raises(RuntimeError, match="P2P exchange unavailable.*no peer access"):
+        P2PExchange(Broken(), 1, 0)
