@@ -1,16 +1,13 @@
 #!/bin/bash
 # re-capture after tuned.json switched fast waves and advection to UNIFORM_WARP; then the bench line
 mkdir -p gpurun_out
-for K in fastwaves advection; do
+for K in diffusion fastwaves advection; do
   CMD="python tools/profile_candidate.py $K {} 3"
   $CMD > gpurun_out/r2_ncu_plain_$K.log 2>&1 || { echo "plain run of $K failed"; continue; }
   N=1; [ $K = fastwaves ] && N=2
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:absinthe_ -s $((2 * N)) -c $N -f -o gpurun_out/r2_prof_$K $CMD > gpurun_out/r2_ncu_full_$K.log 2>&1
   echo "$K ncu exit $?"
 done
-timeout 900 python bench.py --steps 20 --warmup 3 > gpurun_out/r2_bench_1gpu_d.json 2> gpurun_out/r2_bench_1gpu_d.err
-echo "bench rc $?"; python -c "
-import json; d=json.loads(open('gpurun_out/r2_bench_1gpu_d.json').read().strip().splitlines()[-1])
-print(d['value'], d['ms_per_step'], d['roofline']['kernel'], d['roofline']['frac'], {k[:12]: v['kernel_ms'] for k, v in d['breakdown'].items()}, 'sustained', d['sustained']['ms_per_step'], d['sustained']['frac'], 'e2e', d['e2e']['ms_per_step'], d['extras']['advection:auto'])"
+true
 python bench.py --steps 2 --warmup 1 --no-cpu --no-extras --sustain 0 > /dev/null 2>&1 && timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-cpu --no-extras --sustain 0 > gpurun_out/r2_ncu_list.log 2>&1
 echo "launch list exit $?"
