@@ -120,6 +120,7 @@ class ColumnPlan:
             self.O = tuple(g[1] for g in geo)
             self.tiles = self.N[0] * self.N[1] * self.N[2]
         self._geometry(col.get("SLOTS"))
+        self._cluster(col)
         self._arguments()
 
     # -- schedule ---------------------------------------------------------------------------
@@ -291,6 +292,31 @@ class ColumnPlan:
         assert self.smem_bytes <= SMEM_LIMIT, "column ring (%d slots of %d B) exceeds shared memory" % (
             self.ns, self.slot_doubles * 8)
 
+    def _cluster(self, col):
+        """CLUSTER: (CX, CY) -- the CTAs of a thread-block cluster take the CX x CY tiles of one *super-tile* and
+        their TMA producers stay within SLACK ring slots of each other (one remote ``mbarrier`` arrive per peer and
+        slot, template_column.cu).  Neighbouring columns stage overlapping boxes -- the halo lanes and rows, the
+        16-byte rule, partly used DRAM lines: 1.56x the input bytes on fused fast waves -- and persistent CTAs that
+        are left alone drift apart by more planes than the L2 holds, so every CTA fetched its halo from HBM.  Kept
+        within a few planes of each other, the CTAs of a cluster find each other's halo in L2.  Needs work items
+        that are whole columns of one shape (MERGE), full-domain programs (not the training loop)."""
+        want = col.get("CLUSTER") or (1, 1)
+        cx, cy = (int(want[0]), int(want[1])) if not isinstance(want, int) else (int(want), 1)
+        cx, cy = max(1, min(cx, self.N[0])), max(1, min(cy, self.N[1]))
+        usable = (cx * cy > 1 and cx * cy <= 8 and self.nsub == (1, 1, 1) and self.N[2] == 1
+                  and not self.program.get("TRAINING") and not self.wave_sync)
+        self.cluster = (cx, cy) if usable else (1, 1)
+        self.cluster_size = self.cluster[0] * self.cluster[1]
+        self.slack = max(1, int(col.get("SLACK", 4)))          # ring slots a producer may run ahead of its peers
+        self.super = (A.ceil_div(self.N[0], self.cluster[0]), A.ceil_div(self.N[1], self.cluster[1]))
+        # every work item of a cluster kernel has the same number of ring slots (the tick protocol counts them)
+        self.item_chunks = A.ceil_div(self.S[2] - self.kmin, self.kc)
+        if self.cluster_size > 1:
+            ticks = 2 * self.slack + 1
+            self.tick_offset = self.smem_bytes - 48 + 16       # behind full[] / empty[]
+            self.smem_bytes = self.tick_offset + 8 * ticks + 48
+            assert self.smem_bytes <= SMEM_LIMIT, "column ring plus cluster barriers exceed shared memory"
+
     def _arguments(self):
         off = 0
         self.args = []
@@ -367,6 +393,10 @@ class ColumnPlan:
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "FUSE_HALO": self.fuse_halo,
             "FRONT": FRONT_SLACK, "CARRIED": self.carried, "BODY": self._body(),
             "STREAM_STORES": bool(self.opts["STORE_CS"]), "LEADS": self.lead,
+            "CLUSTER": self.cluster_size if self.cluster_size > 1 else 0, "CX": self.cluster[0], "CY": self.cluster[1],
+            "SNX": self.super[0], "SN_TOTAL": self.super[0] * self.super[1], "SLACK": self.slack,
+            "TICKS": 2 * self.slack + 1, "TICK_OFFSET": getattr(self, "tick_offset", 0),
+            "ITEM_CHUNKS": self.item_chunks,
         }
 
     # -- verification on symbolic tags ---------------------------------------------------------

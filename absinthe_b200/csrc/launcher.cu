@@ -54,6 +54,7 @@ struct Driver {
     CUresult (*ModuleGetFunction)(CUfunction*, CUmodule, const char*) = nullptr;
     CUresult (*FuncSetAttribute)(CUfunction, CUfunction_attribute, int) = nullptr;
     CUresult (*OccupancyMaxActiveBlocksPerMultiprocessor)(int*, CUfunction, int, size_t) = nullptr;
+    CUresult (*OccupancyMaxActiveClusters)(int*, CUfunction, const CUlaunchConfig*) = nullptr;   // optional
     CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned,
                              unsigned, CUstream, void**, void**) = nullptr;
     CUresult (*TensorMapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
@@ -90,6 +91,7 @@ int driver_resolve_all() {
     if ((rc = resolve("cuLaunchKernel", g_drv.LaunchKernel))) return rc;
     if ((rc = resolve("cuTensorMapEncodeTiled", g_drv.TensorMapEncodeTiled))) return rc;
     if ((rc = resolve("cuGetErrorString", g_drv.GetErrorString))) return rc;
+    if (resolve("cuOccupancyMaxActiveClusters", g_drv.OccupancyMaxActiveClusters)) g_drv.OccupancyMaxActiveClusters = nullptr;
     if (resolve("cuStreamWaitValue64", g_drv.StreamWaitValue64) || resolve("cuStreamWriteValue64", g_drv.StreamWriteValue64))
         g_drv.StreamWaitValue64 = nullptr, g_drv.StreamWriteValue64 = nullptr;
     g_error.clear();
@@ -401,6 +403,8 @@ struct Group {
     size_t scratch_bytes = 0;      // per resident CTA
     int training_step = 20;
     int fused_halo = 0;
+    int cluster = 1;               // CTAs per thread-block cluster (compiled into the kernel as __cluster_dims__)
+    int max_clusters = 0;          // co-resident clusters of the device (0: not a cluster kernel)
     std::vector<Arg> args;
     std::vector<int> halo_fields;
     CUfunction fn = nullptr;
@@ -554,6 +558,7 @@ int parse_descriptor(absinthe_variant* v, const char* text) {
                 else if (tok == "scratch") ls >> group->scratch_bytes;
                 else if (tok == "training_step") ls >> group->training_step;
                 else if (tok == "fused_halo") ls >> group->fused_halo;
+                else if (tok == "cluster") ls >> group->cluster;
                 else return fail(-2, "descriptor: unknown group attribute '%s'", tok.c_str());
             }
         } else if (key == "arg") {
@@ -627,6 +632,13 @@ int encode_map(const absinthe_variant* v, const Arg& a, double* base, CUtensorMa
 
 int grid_for(const absinthe_variant* v, const Group& g, int tiles) {
     int resident = std::max(1, g.blocks_per_sm) * v->sms;
+    if (g.cluster > 1) {
+        // a cluster kernel walks super-tiles of `cluster` tiles: the grid is a whole number of clusters, all of
+        // them resident at once (a GPC whose SM count is no multiple of the cluster size leaves SMs idle)
+        int clusters = g.max_clusters > 0 ? g.max_clusters : resident / g.cluster;
+        clusters = std::min(clusters, (tiles + g.cluster - 1) / g.cluster);
+        return std::max(1, clusters) * g.cluster;
+    }
     return std::max(1, std::min(tiles, resident));
 }
 
@@ -668,6 +680,8 @@ void set_tilectl(Group& g, int step, int count) {
 }
 
 int launch_group(absinthe_variant* v, Group& g, bool training, cudaStream_t stream) {
+    if (training && g.cluster > 1)
+        return fail(-4, "kernel %s walks super-tiles of a thread-block cluster: no training loop over single tiles", g.symbol.c_str());
     int step = training ? g.training_step : 1;
     int count = (g.tiles + step - 1) / step;
     set_tilectl(g, step, count);
@@ -743,6 +757,28 @@ int absinthe_variant_load(const char* descriptor, const void* cubin, size_t cubi
         r = g_drv.OccupancyMaxActiveBlocksPerMultiprocessor(&blocks, g.fn, g.threads, g.smem);
         if (r != CUDA_SUCCESS || blocks < 1) return give_up(fail(r != CUDA_SUCCESS ? (int)r : -4, "kernel %s cannot be resident (threads %d, smem %zu)", g.symbol.c_str(), g.threads, g.smem));
         g.blocks_per_sm = blocks;
+        if (g.cluster > 1) {
+            if (g.cluster > 8) return give_up(fail(-4, "kernel %s: cluster of %d CTAs exceeds the portable limit of 8", g.symbol.c_str(), g.cluster));
+            g.max_clusters = std::max(1, blocks * v->sms / g.cluster);
+            if (g_drv.OccupancyMaxActiveClusters) {
+                CUlaunchAttribute attr{};
+                attr.id = CU_LAUNCH_ATTRIBUTE_CLUSTER_DIMENSION;
+                attr.value.clusterDim.x = (unsigned)g.cluster;
+                attr.value.clusterDim.y = attr.value.clusterDim.z = 1;
+                CUlaunchConfig cfg{};
+                cfg.gridDimX = (unsigned)(g.max_clusters * g.cluster);
+                cfg.gridDimY = cfg.gridDimZ = 1;
+                cfg.blockDimX = (unsigned)g.threads;
+                cfg.blockDimY = cfg.blockDimZ = 1;
+                cfg.sharedMemBytes = (unsigned)g.smem;
+                cfg.attrs = &attr;
+                cfg.numAttrs = 1;
+                int clusters = 0;
+                r = g_drv.OccupancyMaxActiveClusters(&clusters, g.fn, &cfg);
+                if (r != CUDA_SUCCESS || clusters < 1) return give_up(fail(r != CUDA_SUCCESS ? (int)r : -4, "kernel %s: no cluster of %d CTAs can be resident: %s", g.symbol.c_str(), g.cluster, r != CUDA_SUCCESS ? drv_error(r) : "0 clusters"));
+                g.max_clusters = std::min(g.max_clusters, clusters);
+            }
+        }
         if (g.scratch_bytes) {
             size_t total = g.scratch_bytes * (size_t)grid_for(v, g, g.tiles);
             e = cudaMalloc(&g.scratch, total);

@@ -64,7 +64,9 @@ DEFAULTS = {
                                  # "auto": column kernel for groups whose stencils read each other across k
     "COLUMN": None,              # column kernel shape: {"WARPS": (WX, WY), "PLANES": planes per TMA box, "SLOTS": ring,
                                  # "UNROLL": ring slots per loop trip, "MERGE": walk whole columns of the kernel's own
-                                 # shape instead of the variant's tiles, "WAVE_SYNC": see column.py}
+                                 # shape instead of the variant's tiles, "CLUSTER": (CX, CY) tiles per thread-block
+                                 # cluster whose producers stay within "SLACK" ring slots of each other (halo
+                                 # sharing through L2), "WAVE_SYNC": see column.py}
     "PREFETCH": 2,               # STREAM_K: input planes in flight beyond the ones being read
 }
 FRONT_SLACK = 16                 # doubles before the first box (halo lanes of a warp read below it)
@@ -707,10 +709,11 @@ class Plan:
             lines.append("field %s tmp" % name)
         for g in self.groups:
             lines.append("group %d kernel %s threads %d smem %d tiles %d params %d "
-                         "training_step %d fused_halo %d%s" % (
+                         "training_step %d fused_halo %d%s%s" % (
                              g.id, g.kernel_name, g.launch_threads, g.smem_bytes, g.tiles, g.params_bytes,
                              training.get("STRIDE", 20), int(g.fuse_halo),
-                             " scratch %d" % g.scratch_bytes if getattr(g, "scratch_bytes", 0) else ""))
+                             " scratch %d" % g.scratch_bytes if getattr(g, "scratch_bytes", 0) else "",
+                             " cluster %d" % g.cluster_size if getattr(g, "cluster_size", 1) > 1 else ""))
             for kind, off, name, dim in g.args:
                 if kind == "tmap":
                     lines.append("arg tmap %d %s %d %d %d" % (off, name, dim[0], dim[1], dim[2]))

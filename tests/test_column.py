@@ -104,3 +104,30 @@ def test_merge_walks_columns_of_the_kernels_own_shape():
     assert g.N == (3, 11, 1) and g.T == (43, 6, 60) and g.nsub == (1, 1, 1)     # 2 strips of 30 columns, 3 x 2 rows
     assert g.simulate() == len(g.outputs) * g.rj * g.useful * (4 - g.kmin)
     assert "tiles 33 " in Plan(P.clone(q)).descriptor_text()
+
+
+def test_cluster_kernels_walk_super_tiles(tmp_path):
+    """COLUMN.CLUSTER: CX x CY neighbouring tiles per thread-block cluster; the producers pace each other through
+    remote mbarrier arrives.  Only for merged columns of full-domain programs."""
+    q = P.make_program("fastwaves", [F], [(9, 16, 6)], domain=(128, 64, 60))
+    q["CUDA"] = {"STREAM_K": "regs", "COLUMN": {"WARPS": (2, 3), "MERGE": True, "CLUSTER": (2, 2), "SLACK": 3}}
+    g = Plan(q).groups[0]
+    assert g.N == (3, 22, 1) and g.cluster == (2, 2) and g.super == (2, 11) and g.item_chunks == 60 - g.kmin
+    assert g.smem_bytes - g.tick_offset >= 8 * (2 * 3 + 1)
+    source, descriptor, flags = render("template_tiling.cu", q)
+    assert "__cluster_dims__(4, 1, 1)" in source and "mbar_arrive_remote(&tick[" in source
+    assert " cluster 4" in descriptor
+    path = tmp_path / "cluster.cu"
+    path.write_text(source)
+    proc = subprocess.run(nvcc_command(flags, str(path), str(tmp_path / "cluster.cubin")), capture_output=True, text=True)
+    assert proc.returncode == 0, proc.stderr[-2000:]
+    sass = subprocess.run(["cuobjdump", "-sass", str(tmp_path / "cluster.cubin")], capture_output=True, text=True).stdout
+    # cluster barrier at start-up, remote arrives on the peers' tick barriers
+    assert "UCGABAR_ARV" in sass and "UCGABAR_WAIT" in sass and "SYNCS.ARRIVE.TRANS64.RED" in sass
+    # without MERGE (sub-tiles / k-tiles differ per work item) and for the training loop: plain column kernel
+    q["CUDA"]["COLUMN"] = {"WARPS": (2, 3), "CLUSTER": (2, 2)}
+    g = Plan(P.clone(q)).groups[0]
+    assert g.cluster == (1, 1) and " cluster " not in Plan(P.clone(q)).descriptor_text()
+    t = P.training_program("fitddr", "IN2BD1", (10, 3, 4), cores=3)
+    t["CUDA"] = {"STREAM_K": "regs", "COLUMN": {"MERGE": True, "CLUSTER": (2, 1)}}
+    assert all(getattr(g, "cluster", (1, 1)) == (1, 1) for g in Plan(t).groups)

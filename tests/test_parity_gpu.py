@@ -45,6 +45,13 @@ OPTIONS = [
     ("column-auto", {"STREAM_K": "auto", "INLINE": "all", "BLOCK": (2, 1), "SHUFFLE": True, "FUSE_HALO": True}),
     ("column-merge", {"STREAM_K": "auto", "INLINE": "all", "BLOCK": (1, 1), "FUSE_HALO": True, "THREADS": 128,
                       "COLUMN": {"MERGE": True, "WARPS": (1, 3), "UNROLL": 1}}),
+    ("column-cluster2", {"STREAM_K": "regs", "BLOCK": (1, 1), "FUSE_HALO": True, "THREADS": 128,
+                         "COLUMN": {"MERGE": True, "WARPS": (1, 3), "UNROLL": 1, "CLUSTER": (2, 1), "SLACK": 2}}),
+    ("column-cluster2x2-planes2", {"STREAM_K": "regs", "BLOCK": (2, 1), "FUSE_HALO": True,
+                                   "COLUMN": {"MERGE": True, "WARPS": (1, 2), "PLANES": 2, "SLOTS": 2, "CLUSTER": (2, 2),
+                                              "SLACK": 1}}),
+    ("column-cluster1x8", {"STREAM_K": "regs", "BLOCK": (1, 1),
+                           "COLUMN": {"MERGE": True, "WARPS": (2, 2), "UNROLL": 1, "CLUSTER": (1, 8)}}),
     ("column-rj2-planes2-halo", {"STREAM_K": "regs", "BLOCK": (2, 1), "COLUMN": {"WARPS": (1, 2), "PLANES": 2},
                                  "FUSE_HALO": True}),
     ("column-rj3-planes3", {"STREAM_K": "regs", "BLOCK": (3, 1),
