@@ -50,7 +50,10 @@ def main():
     build_only = "--prebuild" in args
     check = "--check" in args
     args = [a for a in args if a not in ("--prebuild", "--check")]
-    kernel, overrides = args[0], [json.loads(a) for a in args[1:]]
+    texts = []
+    for a in args[1:]:                      # "@file": one JSON option set per line
+        texts += [line for line in open(a[1:]).read().splitlines() if line.strip()] if a.startswith("@") else [a]
+    kernel, overrides = args[0], [json.loads(t) for t in texts]
     if build_only:
         with ProcessPoolExecutor(max_workers=os.cpu_count() or 4) as pool:
             for line in pool.map(prebuild, [(kernel, extra) for extra in overrides]):
