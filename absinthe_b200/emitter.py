@@ -55,6 +55,8 @@ DEFAULTS = {
     "UNIFORM_WARP": False,       # warp index through __shfl_sync(.., 0): the compiler then knows that the role
                                  # split and the per-warp task loops are warp-uniform (uniform datapath, no
                                  # re-materialised descriptors in "divergent" code)
+    "STORE_PTR": False,          # one global address per output and thread, the points of its block at constant offsets
+                                 # (instead of one 64-bit index computation per point and output)
     "FAST_PATH": True,           # unclipped sub-tiles take a copy of the code with compile-time ranges (twice the code)
     "WAIT_SLEEP": 0,             # ns a starved consumer backs off between mbarrier polls
     "L2_PREFETCH": 0,            # work items whose boxes are prefetched into L2 ahead of the ring
@@ -631,7 +633,7 @@ class GroupPlan:
             "PARAMS_BYTES": self.params_bytes, "NAMES": self.names, "INLINED": sorted(self.inlined),
             "BLOCK": self.block, "FUSE_HALO": self.fuse_halo, "FRONT": self.front,
             "WARPS": self.threads // 32, "LAUNCH_THREADS": self.launch_threads,
-            "FAST_PATH": bool(self.opts["FAST_PATH"]), "STREAM_STORES": bool(self.opts["STORE_CS"]), "UNIFORM_WARP": bool(self.opts["UNIFORM_WARP"]), "POLL_WARP": bool(self.opts["POLL_WARP"]), "L2_PREFETCH": int(self.opts["L2_PREFETCH"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
+            "FAST_PATH": bool(self.opts["FAST_PATH"]), "STORE_PTR": bool(self.opts["STORE_PTR"]), "STREAM_STORES": bool(self.opts["STORE_CS"]), "UNIFORM_WARP": bool(self.opts["UNIFORM_WARP"]), "POLL_WARP": bool(self.opts["POLL_WARP"]), "L2_PREFETCH": int(self.opts["L2_PREFETCH"]), "STREAM": self.stream, "KMIN": getattr(self, "kmin", 0), "PREFETCH": getattr(self, "prefetch", 0),
             "FIRST_BYTES": getattr(self, "first_bytes", 0), "NB": self.stages,
         }
 

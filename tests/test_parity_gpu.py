@@ -37,6 +37,10 @@ OPTIONS = [
     ("uniform-warp", {"INLINE": "all", "SHUFFLE": True, "BLOCK": (2, 1), "FUSE_HALO": True, "UNIFORM_WARP": True}),
     ("uniform-warp-stream-k", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True,
                                "UNIFORM_WARP": True}),
+    ("store-ptr", {"INLINE": "all", "SHUFFLE": True, "BLOCK": (4, 1), "FUSE_HALO": True, "UNIFORM_WARP": True,
+                   "FAST_PATH": False, "STORE_PTR": True}),
+    ("store-ptr-generic-cs", {"BLOCK": (2, 2), "STORE_PTR": True, "STORE_CS": True, "THREADS": 128}),
+    ("store-ptr-stream-k", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "STORE_PTR": True}),
     ("stream-k", {"STREAM_K": True}),
     ("stream-k-inline", {"STREAM_K": True, "INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "PREFETCH": 1}),
     ("poll-warp", {"INLINE": "all", "BLOCK": (2, 1), "FUSE_HALO": True, "POLL_WARP": True, "STAGES": 3}),
