@@ -91,3 +91,27 @@ def test_variant_on_another_device_than_the_current_one(launcher_lib):
     for name, want in zip(oracle.outputs, expected):
         assert outs[v.outputs.index(name)].cpu().numpy().tobytes() == want.tobytes()
     v.close()
+
+
+def test_cluster_kernels_launch_whole_clusters_and_refuse_the_training_loop(launcher_lib, tmp_path):
+    """COLUMN.CLUSTER: the grid is a whole number of co-resident clusters (graph replay included), results are the
+    oracle's, and the training loop over single tiles is refused; a cluster beyond the portable size is a load error."""
+    import re
+    from common import assert_bit_exact
+    f = P.KERNELS["fastwaves"][1]()
+    program = P.make_program("fastwaves", [f], [(2, 4, 6)], domain=(70, 26, 12))     # 3 x 13 tiles: dead ranks in x and y
+    program["CUDA"] = {"STREAM_K": "regs", "FUSE_HALO": True,
+                       "COLUMN": {"MERGE": True, "WARPS": (1, 2), "UNROLL": 1, "CLUSTER": (2, 2), "SLACK": 1}}
+    assert_bit_exact(program)
+    assert_bit_exact(program, graph=True)
+    v = Variant.from_program(P.clone(program))
+    v.bind([v.empty_field() for _ in v.inputs], [v.empty_field() for _ in v.outputs])
+    with pytest.raises(LauncherError, match="training loop"):
+        v.run(1, flush=False, training=True)
+    v.run(2, flush=False)
+    v.close()
+    desc, cubin = build_variant(P.clone(program))
+    big = tmp_path / "big.desc"
+    big.write_text(re.sub(r"cluster \d+", "cluster 16", open(desc).read()))
+    with pytest.raises(LauncherError, match="portable limit"):
+        Variant(str(big), cubin)
