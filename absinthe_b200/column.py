@@ -22,7 +22,10 @@ memory costs a CTA barrier per phase and plane.  A *column* kernel removes both:
   plane has been consumed and almost the whole ring is in flight;
 * the TMA producer warp delivers, per ring slot, one ``DX x DY x KC`` box per input (``KC`` planes per
   request); consumer warps meet the producer through ``full[]/empty[]`` mbarriers once per slot and
-  never meet each other.
+  never meet each other;
+* optionally (``COLUMN.CLUSTER``) the kernel runs in thread-block clusters: the CTAs of a cluster take
+  neighbouring tiles and their producers pace each other through remote ``mbarrier`` arrives, so the
+  halo cells two columns share are fetched from HBM once (``_cluster`` below).
 
 The plan is built as a small IR (``ops`` + ``carries``) from which the CUDA text is rendered;
 ``simulate`` replays the IR on symbolic tags (which stencil / column / row / plane a register holds),
