@@ -53,7 +53,11 @@ int absinthe_device_count(void);
 /* ---- variant life cycle ------------------------------------------------------------------ */
 
 /* descriptor: NUL-terminated text written next to the .cu by generate_code (the .desc file);
- * cubin: image compiled from the generated .cu for sm_100a. */
+ * cubin: image compiled from the generated .cu for sm_100a.  A group line of the descriptor names the
+ * kernel and its launch shape (threads, dynamic shared memory, tile count, parameter-block size) and
+ * optionally `scratch <bytes per CTA>` and `cluster <CTAs>`: a kernel compiled for thread-block clusters
+ * is launched as a whole number of co-resident clusters and is refused by the training loop of
+ * absinthe_variant_run. */
 int absinthe_variant_load(const char* descriptor, const void* cubin, size_t cubin_bytes,
                           int device, absinthe_variant** out);
 void absinthe_variant_free(absinthe_variant* v);
